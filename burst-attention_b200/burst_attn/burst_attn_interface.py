@@ -1,0 +1,272 @@
+"""Public API and ring drivers: ``burst_attn_func`` / ``burst_attn_func_striped``
+with the reference's positional signature (burst_attn_interface.py:109-158), as
+``torch.autograd.Function``s ``OpBurstAttn`` / ``OpBurstAttnStrip`` (:161-613).
+
+What is the same as the reference: names, argument order and defaults, shard
+layouts (contiguous / zigzag halves / striped, test/test_burst.py:44-58), the
+ring schedules (forward: K/V rotate, :214-242; backward: the Q-bundle
+(delta, dO, Q, lse) rotates and the partial dQ rides one hop behind it,
+:291-396), output dtype, the assertion that causal needs flash == "cuda".
+
+What is B200-native instead: every round is ONE kernel launch of the
+C-ABI library (carried (O, lse) state and fp32 dQ/dK/dV accumulation fused into
+the tile kernels; half-sequence and shifted cases are pointer/length views or a
+causal offset, never ``.contiguous()`` copies); user tensors are never used as
+receive buffers; the ring hop is grouped NCCL send/recv on a side stream posted
+before the round's kernel and awaited after it.
+"""
+from __future__ import annotations
+
+import math
+from typing import List
+
+import torch
+
+from .chunk_ops import get_ops
+from .comm import Ring, get_rank, get_world_size
+
+__all__ = ["burst_attn_func", "burst_attn_func_striped", "OpBurstAttn", "OpBurstAttnStrip",
+           "get_partition_id", "split2_gethalf"]
+
+
+def get_partition_id(double_group, r):
+    """Offset of the shard held in round ``r`` (reference :20-37).  The flat ring
+    used here is the ``double_group[0] is None`` branch: ``r - 1``."""
+    return r - 1
+
+
+def split2_gethalf(inp, first_dim, half_idx=0):
+    """Half-sequence VIEW (reference :96-106); never copied here."""
+    dim = 1 if first_dim else 2
+    n = inp.shape[dim] // 2
+    return inp.narrow(dim, 0, n) if half_idx == 0 else inp.narrow(dim, n, inp.shape[dim] - n)
+
+
+def _half(t, dim, idx):
+    n = t.shape[dim] // 2
+    return t.narrow(dim, 0, n) if idx == 0 else t.narrow(dim, n, t.shape[dim] - n)
+
+
+def _check_inputs(q, k, v, seq_dim):
+    assert q.dim() == 4 and k.shape == v.shape and q.shape[0] == k.shape[0] and q.shape[3] == k.shape[3], \
+        "q, k, v must be 4-D with matching batch and head_dim"
+    assert q.shape[3 - seq_dim] == k.shape[3 - seq_dim], "q and k/v must have the same number of heads"
+    assert q.dtype == k.dtype == v.dtype, "q, k, v must share a dtype"
+
+
+# --------------------------------------------------------------------------- #
+# forward ring (reference OpBurstAttn.forward :171-253, OpBurstAttnStrip.forward :411-493)
+# --------------------------------------------------------------------------- #
+def _ring_forward(q, k, v, scale, seq_dim, mode, process_group):
+    """mode: "none" (non-causal) | "zigzag" | "striped".  Returns (out, lse[B,H,S] fp32)."""
+    ops = get_ops()
+    ring = Ring(process_group, tag="ring")
+    W, i = ring.world_size, ring.rank
+    B, S, H = q.shape[0], q.shape[seq_dim], q.shape[3 - seq_dim]
+    if mode == "zigzag":
+        assert S % 2 == 0, "zigzag causal sharding needs an even local sequence length"
+    out = torch.empty_like(q)
+    lse = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
+    o_acc = torch.empty(q.shape, dtype=torch.float32, device=q.device) if W > 1 else None
+    if W > 1:
+        k, v = k.contiguous(), v.contiguous()
+    recv = [[torch.empty_like(k), torch.empty_like(v)] for _ in range(min(2, W - 1))]
+    cur_k, cur_v = k, v
+    for r in range(1, W + 1):
+        j = (i - get_partition_id([None, None], r)) % W  # source rank of the held K/V (App. B)
+        if r != W:
+            nxt = recv[(r - 1) % len(recv)]
+            ring.post([cur_k, cur_v], nxt)
+        first, last = r == 1, r == W
+        if mode == "none":
+            ops.fwd_chunk(q, cur_k, cur_v, o_acc, lse, out, scale, False, 0, first, last, seq_dim)
+        elif mode == "zigzag":
+            if r == 1:  # own shard: plain causal (:221-224)
+                ops.fwd_chunk(q, cur_k, cur_v, o_acc, lse, out, scale, True, 0, first, last, seq_dim)
+            elif j < i:  # split_kv: all Q x first half of K/V (:225-231)
+                ops.fwd_chunk(q, _half(cur_k, seq_dim, 0), _half(cur_v, seq_dim, 0), o_acc, lse, out, scale,
+                              False, 0, False, last, seq_dim)
+            else:  # second half of Q x all K/V, merged into the second half of the state (:232-235)
+                ops.fwd_chunk(_half(q, seq_dim, 1), cur_k, cur_v, _half(o_acc, seq_dim, 1), _half(lse, 2, 1),
+                              _half(out, seq_dim, 1), scale, False, 0, False, last, seq_dim)
+                if last:  # rows the last round did not visit: hand their finished state over
+                    ops.cast(_half(o_acc, seq_dim, 0), _half(out, seq_dim, 0), seq_dim)
+        elif mode == "striped":
+            # source rank ahead of us -> strictly-lower-triangular (causal_shift, :454,:463-475)
+            ops.fwd_chunk(q, cur_k, cur_v, o_acc, lse, out, scale, True, -1 if j > i else 0, first, last, seq_dim)
+        else:
+            raise ValueError(mode)
+        if r != W:
+            ring.wait()
+            cur_k, cur_v = nxt
+    return out, lse
+
+
+# --------------------------------------------------------------------------- #
+# backward ring (reference OpBurstAttn.backward :256-398, OpBurstAttnStrip.backward :496-613)
+# --------------------------------------------------------------------------- #
+def _ring_backward(d_o, q, k, v, out, lse, scale, seq_dim, mode, process_group, deterministic):
+    ops = get_ops()
+    ring = Ring(process_group, tag="ring")
+    W, i = ring.world_size, ring.rank
+    dev = q.device
+    q, k, v, d_o, out = (t.contiguous() for t in (q, k, v, d_o, out))
+    B, S, H = q.shape[0], q.shape[seq_dim], q.shape[3 - seq_dim]
+
+    # delta always travels instead of O (the reference's optimize_bwd_comm, :271-278):
+    # 4 B instead of 2*D B per row and head, and the tile kernel never needs O.
+    delta = torch.empty((B, H, S), dtype=torch.float32, device=dev)
+    ops.delta(out, d_o, delta, seq_dim)
+
+    f32 = dict(dtype=torch.float32, device=dev)
+    dk_acc = torch.zeros(k.shape, **f32)
+    dv_acc = torch.zeros(v.shape, **f32)
+    part = torch.zeros(q.shape, **f32)  # this round's dQ partial (the kernel reduce-adds into it)
+
+    def round_kernel(r, j, bundle, dq_part):
+        dlt, g, qq, ls = bundle
+        if mode == "none":
+            ops.bwd_chunk(g, qq, k, v, dlt, ls, dq_part, dk_acc, dv_acc, scale, False, 0, seq_dim, deterministic)
+        elif mode == "zigzag":
+            if r == 1:
+                ops.bwd_chunk(g, qq, k, v, dlt, ls, dq_part, dk_acc, dv_acc, scale, True, 0, seq_dim, deterministic)
+            elif j < i:  # split_q: second half of the bundle x all K/V (:322-345,:383-386)
+                ops.bwd_chunk(_half(g, seq_dim, 1), _half(qq, seq_dim, 1), k, v, _half(dlt, 2, 1), _half(ls, 2, 1),
+                              _half(dq_part, seq_dim, 1), dk_acc, dv_acc, scale, False, 0, seq_dim, deterministic)
+            else:  # whole bundle x first half of K/V (:347-367,:387-390)
+                ops.bwd_chunk(g, qq, _half(k, seq_dim, 0), _half(v, seq_dim, 0), dlt, ls, dq_part,
+                              _half(dk_acc, seq_dim, 0), _half(dv_acc, seq_dim, 0), scale, False, 0, seq_dim,
+                              deterministic)
+        elif mode == "striped":
+            # K/V home on i, bundle from j: strict iff j < i (causal_shift, :529)
+            ops.bwd_chunk(g, qq, k, v, dlt, ls, dq_part, dk_acc, dv_acc, scale, True, -1 if j < i else 0, seq_dim,
+                          deterministic)
+        else:
+            raise ValueError(mode)
+
+    bundle = [delta, d_o, q, lse.contiguous()]
+    if W == 1:
+        round_kernel(1, i, bundle, part)
+        dq_final = part
+    else:
+        recv = [[torch.empty_like(t) for t in bundle] for _ in range(min(2, W - 1))]
+        hold = None                      # fp32 dQ accumulated for the bundle held in the previous round
+        spare = [torch.empty(q.shape, **f32), torch.empty(q.shape, **f32)]
+        for r in range(1, W + 1):
+            j = (i - get_partition_id([None, None], r)) % W
+            srcs: List[torch.Tensor] = []
+            dsts: List[torch.Tensor] = []
+            if r != W:  # bundle hop (:295-299)
+                nxt = recv[(r - 1) % len(recv)]
+                srcs += bundle
+                dsts += nxt
+            if r != 1:  # dQ hop, one behind its bundle (:300-302)
+                inbound = spare.pop()
+                srcs.append(hold)
+                dsts.append(inbound)
+            if srcs:
+                ring.post(srcs, dsts)
+            round_kernel(r, j, bundle, part)
+            if srcs:
+                ring.wait()
+            if r != W:
+                bundle = nxt
+            if r == 1:
+                hold, part = part, spare.pop()
+                part.zero_()
+            else:
+                ops.accumulate(part, inbound, seq_dim)  # dq += buf (:379-390), in fp32
+                spare.append(hold)
+                hold = inbound
+                if r != W:
+                    part.zero_()
+        # final hop home (:393-396)
+        dq_final = spare.pop()
+        ring.post([hold], [dq_final])
+        ring.wait()
+
+    dq = torch.empty_like(q)
+    dk = torch.empty_like(k)
+    dv = torch.empty_like(v)
+    ops.cast(dq_final, dq, seq_dim)
+    ops.cast(dk_acc, dk, seq_dim)
+    ops.cast(dv_acc, dv, seq_dim)
+    return dq, dk, dv
+
+
+# --------------------------------------------------------------------------- #
+def _prepare(ctx, q, k, v, softmax_scale, flash, causal, optimize_bwd_comm, deterministic, process_group,
+             double_group):
+    if isinstance(double_group[0], tuple):  # (group, dq_group) pairs (:188-194): one flat ring serves both
+        double_group = (double_group[0][0], double_group[1][0])
+    assert not causal or flash == "cuda", "Causal attention only supported for Flash v2"
+    ctx.softmax_scale = 1 / math.sqrt(q.shape[-1]) if softmax_scale is None else softmax_scale
+    ctx.flash = None if flash not in ["cuda", "triton"] else flash
+    ctx.seq_dim = 1 if ctx.flash else 2
+    ctx.causal = causal
+    ctx.optimize_bwd_comm = optimize_bwd_comm  # delta always travels; kept for API parity
+    ctx.deterministic = deterministic
+    ctx.process_group = process_group
+    ctx.double_group = double_group
+    _check_inputs(q, k, v, ctx.seq_dim)
+
+
+class OpBurstAttn(torch.autograd.Function):
+    """
+    for Normal Attention (flash=None):  q, k, v: [B, N, S, H]
+    for Flash ("cuda"/"triton"):        q, k, v: [B, S, N, H]
+    Each rank passes its own sequence shard: contiguous when non-causal, zigzag
+    halves {i, 2W-1-i} when causal.
+    """
+
+    @staticmethod
+    def forward(ctx, q, k, v, softmax_scale=None, flash="cuda", causal=False, optimize_bwd_comm=False,
+                deterministic=False, process_group=None, double_group=[None, None]):
+        _prepare(ctx, q, k, v, softmax_scale, flash, causal, optimize_bwd_comm, deterministic, process_group,
+                 double_group)
+        ctx.mode = "zigzag" if causal else "none"
+        out, lse = _ring_forward(q, k, v, ctx.softmax_scale, ctx.seq_dim, ctx.mode, process_group)
+        ctx.save_for_backward(q, k, v, lse, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        q, k, v, lse, out = ctx.saved_tensors
+        dq, dk, dv = _ring_backward(grad_output, q, k, v, out, lse, ctx.softmax_scale, ctx.seq_dim, ctx.mode,
+                                    ctx.process_group, ctx.deterministic)
+        return dq, dk, dv, None, None, None, None, None, None, None
+
+
+class OpBurstAttnStrip(torch.autograd.Function):
+    """Striped-causal variant: rank i owns tokens {i, i+W, i+2W, ...}."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, softmax_scale=None, flash="cuda", causal=False, optimize_bwd_comm=False,
+                deterministic=False, process_group=None, double_group=[None, None]):
+        _prepare(ctx, q, k, v, softmax_scale, flash, causal, optimize_bwd_comm, deterministic, process_group,
+                 double_group)
+        ctx.mode = "striped" if causal else "none"
+        out, lse = _ring_forward(q, k, v, ctx.softmax_scale, ctx.seq_dim, ctx.mode, process_group)
+        ctx.save_for_backward(q, k, v, lse, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        q, k, v, lse, out = ctx.saved_tensors
+        dq, dk, dv = _ring_backward(grad_output, q, k, v, out, lse, ctx.softmax_scale, ctx.seq_dim, ctx.mode,
+                                    ctx.process_group, ctx.deterministic)
+        return dq, dk, dv, None, None, None, None, None, None, None
+
+
+def burst_attn_func_striped(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, softmax_scale: float = None,
+                            flash: str = "cuda", causal: bool = False, optimize_bwd_comm: bool = False,
+                            deterministic: bool = False, process_group=None, double_group=[None, None]):
+    return OpBurstAttnStrip.apply(q, k, v, softmax_scale, flash, causal, optimize_bwd_comm, deterministic,
+                                  process_group, double_group)
+
+
+def burst_attn_func(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, softmax_scale: float = None,
+                    flash: str = "cuda", causal: bool = False, optimize_bwd_comm: bool = False,
+                    deterministic: bool = False, process_group=None, double_group=[None, None]):
+    return OpBurstAttn.apply(q, k, v, softmax_scale, flash, causal, optimize_bwd_comm, deterministic,
+                             process_group, double_group)

@@ -1,0 +1,172 @@
+"""Ring communicator of the burst-attention drivers.
+
+Mirrors the reference's ``Ring`` (comm.py:104-321): ops are queued with
+``double_ring_send_recv`` / ``_ring_send_recv_base``, launched by ``commit`` and
+awaited by ``wait``.  Two transports:
+
+* ``native`` (CUDA tensors, the product path): the C-ABI ring of
+  include/burst_attn_b200.h -- grouped ncclSend/ncclRecv on a library-owned
+  high-priority side stream, event hand-off to the compute stream, no host
+  sync (the reference's BMTrain side-stream variant, comm.py:267-283,313-317,
+  is the model).  One communicator per (process group, tag), cached -- the
+  reference builds a fresh ``Ring`` per call (burst_attn_interface.py:205,265,268).
+* ``torch`` (CPU tensors under gloo, used by the world_size-2 CPU tests of the
+  ring schedule): ``dist.batch_isend_irecv`` as in comm.py:159-171,269.
+
+8 x B200 on one NVSwitch is a uniform fabric, so the intra/inter "double ring"
+(comm.py:187-254) is not needed; ``double_group`` is accepted and served by the
+flat ring over ``process_group`` (same results: only the summation order of the
+rounds changes).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import native as _n
+
+
+def get_world_size(group=None) -> int:
+    if not dist.is_available() or not dist.is_initialized():
+        return 1
+    return dist.get_world_size(group)
+
+
+def get_rank(group=None) -> int:
+    if not dist.is_available() or not dist.is_initialized():
+        return 0
+    return dist.get_rank(group)
+
+
+def replicate(t: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(t)
+    out.copy_(t)
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# native rings, cached per (process group, tag, device)
+# --------------------------------------------------------------------------- #
+class _NativeRing:
+    def __init__(self, group, tag: str, device: torch.device):
+        self.lib = _n.lib()
+        self.world = get_world_size(group)
+        self.rank = get_rank(group)
+        self.handle = ctypes.c_void_p()
+        idbuf = (ctypes.c_uint8 * _n.NCCL_UNIQUE_ID_BYTES)()
+        if self.world > 1:
+            payload = [None]
+            if self.rank == 0:
+                _n.check(self.lib.ba_ring_unique_id(idbuf), "ba_ring_unique_id")
+                payload = [bytes(idbuf)]
+            src = dist.get_global_rank(group, 0) if group is not None else 0
+            dist.broadcast_object_list(payload, src=src, group=group, device=device)
+            ctypes.memmove(idbuf, payload[0], _n.NCCL_UNIQUE_ID_BYTES)
+        with torch.cuda.device(device):
+            _n.check(self.lib.ba_ring_create(idbuf, self.rank, self.world, ctypes.byref(self.handle)),
+                     "ba_ring_create")
+
+    def post(self, srcs: Sequence[torch.Tensor], dsts: Sequence[torch.Tensor]) -> None:
+        n = len(srcs)
+        VP = ctypes.c_void_p * n
+        I64 = ctypes.c_int64 * n
+        for s, d in zip(srcs, dsts):
+            assert s.is_contiguous() and d.is_contiguous() and s.numel() * s.element_size() == d.numel() * d.element_size()
+        src = VP(*[s.data_ptr() for s in srcs])
+        dst = VP(*[d.data_ptr() for d in dsts])
+        nb = I64(*[s.numel() * s.element_size() for s in srcs])
+        _n.check(self.lib.ba_ring_post(self.handle, src, dst, nb, n, _n.stream_ptr(srcs[0].device)), "ba_ring_post")
+
+    def wait(self, device) -> None:
+        _n.check(self.lib.ba_ring_wait(self.handle, _n.stream_ptr(device)), "ba_ring_wait")
+
+
+_native_rings: Dict[Tuple[int, str, int], _NativeRing] = {}
+
+
+def _native_ring(group, tag: str, device: torch.device) -> _NativeRing:
+    key = (id(group) if group is not None else 0, tag, device.index if device.index is not None else -1)
+    ring = _native_rings.get(key)
+    if ring is None:
+        ring = _NativeRing(group, tag, device)
+        _native_rings[key] = ring
+    return ring
+
+
+# --------------------------------------------------------------------------- #
+class Ring:
+    """Single flat ring over ``process_group``: send to (rank+1)%W, receive from (rank-1)%W."""
+
+    def __init__(self, process_group=None, local_group=(None, None), dq: bool = False, tag: Optional[str] = None):
+        self.comm = process_group
+        self.world_size = get_world_size(process_group)
+        self.rank = get_rank(process_group)
+        self.tag = tag or ("dq" if dq else "kv")
+        # double-ring bookkeeping kept for API compatibility (comm.py:137-141)
+        self.local_group, self.local_group2 = local_group[0], local_group[1]
+        self.double_ring = False
+        self.intra_size = self.world_size
+        self.inter_size = 1
+        self._pending: List[Tuple[torch.Tensor, torch.Tensor]] = []
+        self._reqs = []
+        self._native: Optional[_NativeRing] = None
+        self._device = None
+
+    # ---- queue (comm.py:256-257)
+    def _ring_send_recv_base(self, tensor_list, dest_list, group=None):
+        self._pending += list(zip(tensor_list, dest_list))
+
+    def double_ring_send_recv(self, tensor_list, dest_list, r=0):
+        self._ring_send_recv_base(tensor_list, dest_list)
+
+    def double_ring_send_recv_q(self, tensor_list, dest_list, r=0):
+        self._ring_send_recv_base(tensor_list, dest_list)
+
+    # ---- launch (comm.py:285-299)
+    def commit(self):
+        if not self._pending:
+            return
+        srcs = [s for s, _ in self._pending]
+        dsts = [d for _, d in self._pending]
+        self._pending = []
+        if srcs[0].is_cuda:
+            self._device = srcs[0].device
+            if self._native is None:
+                self._native = _native_ring(self.comm, self.tag, self._device)
+            self._native.post(srcs, dsts)
+            self._reqs = ["native"]
+        else:
+            self._reqs = self._commit_torch(srcs, dsts)
+
+    def _commit_torch(self, srcs, dsts):
+        W, rank = self.world_size, self.rank
+        if W == 1:
+            for s, d in zip(srcs, dsts):
+                d.copy_(s)
+            return []
+        nxt, prv = (rank + 1) % W, (rank - 1 + W) % W
+        if self.comm is not None:
+            nxt, prv = dist.get_global_rank(self.comm, nxt), dist.get_global_rank(self.comm, prv)
+        ops = []
+        for s, d in zip(srcs, dsts):
+            send = dist.P2POp(dist.isend, s, nxt, group=self.comm)
+            recv = dist.P2POp(dist.irecv, d, prv, group=self.comm)
+            ops += [send, recv] if rank % 2 == 0 else [recv, send]  # comm.py:166-171
+        return dist.batch_isend_irecv(ops)
+
+    # ---- await (comm.py:301-321)
+    def wait(self, force_wait_inter=False):
+        for r in self._reqs:
+            if r == "native":
+                self._native.wait(self._device)
+            else:
+                r.wait()
+        self._reqs = []
+
+    # ---- convenience used by the drivers
+    def post(self, srcs, dsts):
+        self._ring_send_recv_base(srcs, dsts)
+        self.commit()

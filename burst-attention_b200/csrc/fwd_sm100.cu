@@ -1,0 +1,451 @@
+// ba_fwd_chunk: one ring round of the forward on sm_100a.
+//
+// Replaces, for flash="cuda"/"triton", the reference's per-round
+//   flash_attn_2_cuda.fwd  +  cuda_scale_out_lse_helper          (burst_utils.py:149-177, :20-33)
+// and the Triton LAO tile with carried state                       (lao.py:66-244)
+// by ONE kernel: the carried (O fp32 normalised, lse) state is loaded in the
+// prologue as the initial online-softmax state (m = lse, l = 1, acc = O) and the
+// merged state is written in the epilogue -- no separate merge pass over HBM.
+//
+// Structure (one CTA = two 128-row Q tiles of one (batch, head), ping-ponged):
+//   warp 9      TMA producer: Q once, then K_i / V_i tiles into 2-stage rings
+//   warp 8      single-thread tcgen05.mma issuer:
+//                 S_w = Q_w K_i^T      (SS, both operands K-major SW128 smem)
+//                 O_w += P_w V_i       (TS, P bf16/fp16 in TMEM aliasing S_w, V MN-major smem)
+//   warps 0-3   softmax for Q tile 0 (thread t owns row t == TMEM lane t)
+//   warps 4-7   softmax for Q tile 1
+// TMEM (512 cols): S0 [0,128)  S1 [128,256)  O0 [256,384)  O1 [384,512); P_w = S_w cols [0,64).
+// The O rescale is lazy (only when a row max grows by more than 2^8), done in
+// place by the softmax warps, so it is off the steady-state critical path.
+#include <math.h>
+
+#include "host_common.h"
+#include "sm100_ptx.cuh"
+
+namespace ba {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockN = 128;
+constexpr int kHeadDim = 128;
+constexpr int kKStages = 2;
+constexpr int kVStages = 2;
+constexpr int kTileBytes = kBlockN * kHeadDim * 2;  // 32 KiB: one 128x128 16-bit tile
+constexpr int kBoxBytes = kTileBytes / 2;           // 16 KiB: one 128 x 64 SW128 TMA box
+constexpr int kFwdThreads = 320;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays <= 2^8
+
+struct FwdParams {
+  float* o_acc;
+  int64_t oacc_sb, oacc_ss, oacc_sh;
+  float* lse;
+  int64_t lse_sb, lse_sh;
+  void* o_out;
+  int64_t oout_sb, oout_ss, oout_sh;
+  int B, Sq, Sk, H;
+  float scale_log2;
+  int causal;
+  int causal_off;
+  int load_state;
+  int store_lowp;
+};
+
+struct __align__(8) FwdBarriers {
+  uint64_t q_full;
+  uint64_t k_full[kKStages], k_empty[kKStages];
+  uint64_t v_full[kVStages], v_empty[kVStages];
+  uint64_t s_full[2];   // MMA -> softmax: S_w ready in TMEM
+  uint64_t p_ready[2];  // softmax -> MMA: P_w written (and O_w rescaled)
+  uint64_t o_done[2];   // MMA -> softmax: P_w V accumulated into O_w
+  uint32_t tmem_base;
+};
+
+constexpr int kFwdSmemBytes = 2 * kTileBytes + kKStages * kTileBytes + kVStages * kTileBytes + 1024 /*align*/ +
+                              256 /*barriers*/;
+
+// number of K tiles a 128-row Q tile starting at r0 must visit
+__device__ __forceinline__ int fwd_trip_count(int r0, const FwdParams& p) {
+  if (r0 >= p.Sq) return 0;
+  int r_last = min(r0 + kBlockM - 1, p.Sq - 1);
+  int max_limit = p.causal ? min(r_last + p.causal_off, p.Sk - 1) : p.Sk - 1;
+  return max_limit < 0 ? 0 : max_limit / kBlockN + 1;
+}
+
+template <bool kBF16>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                               // [2][32 KiB]
+  uint8_t* sK = sQ + 2 * kTileBytes;                // [kKStages][32 KiB]
+  uint8_t* sV = sK + kKStages * kTileBytes;         // [kVStages][32 KiB]
+  FwdBarriers* bars = reinterpret_cast<FwdBarriers*>(sV + kVStages * kTileBytes);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int row0 = blockIdx.x * (2 * kBlockM);
+  const int n_t0 = fwd_trip_count(row0, p);
+  const int n_t1 = fwd_trip_count(row0 + kBlockM, p);
+  const int n_max = max(n_t0, n_t1);
+
+  // ---------------------------------------------------------------- setup
+  if (warp == 9 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_init(&bars->q_full, 1);
+      for (int i = 0; i < kKStages; ++i) {
+        mbar_init(&bars->k_full[i], 1);
+        mbar_init(&bars->k_empty[i], 1);
+      }
+      for (int i = 0; i < kVStages; ++i) {
+        mbar_init(&bars->v_full[i], 1);
+        mbar_init(&bars->v_empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bars->s_full[i], 1);
+        mbar_init(&bars->p_ready[i], 4);  // one elected arrive per softmax warp
+        mbar_init(&bars->o_done[i], 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&bars->tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 9) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars->q_full, 2 * kTileBytes);
+      for (int w = 0; w < 2; ++w)
+        for (int half = 0; half < 2; ++half)
+          tma_load_4d(sQ + w * kTileBytes + half * kBoxBytes, &tmQ, &bars->q_full, half * 64, h,
+                      row0 + w * kBlockM, b);
+      for (int i = 0; i < n_max; ++i) {
+        const int ks = i % kKStages, kph = (i / kKStages) & 1;
+        mbar_wait(&bars->k_empty[ks], kph ^ 1);
+        mbar_arrive_expect_tx(&bars->k_full[ks], kTileBytes);
+        for (int half = 0; half < 2; ++half)
+          tma_load_4d(sK + ks * kTileBytes + half * kBoxBytes, &tmK, &bars->k_full[ks], half * 64, h,
+                      i * kBlockN, b);
+        const int vs = i % kVStages, vph = (i / kVStages) & 1;
+        mbar_wait(&bars->v_empty[vs], vph ^ 1);
+        mbar_arrive_expect_tx(&bars->v_full[vs], kTileBytes);
+        for (int half = 0; half < 2; ++half)
+          tma_load_4d(sV + vs * kTileBytes + half * kBoxBytes, &tmV, &bars->v_full[vs], half * 64, h,
+                      i * kBlockN, b);
+      }
+    }
+  } else if (warp == 8) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc(kBF16, kBlockM, kBlockN, false, false);
+      constexpr uint32_t idesc_pv = make_idesc(kBF16, kBlockM, kHeadDim, false, true);
+      const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
+      const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
+      const int n_t[2] = {n_t0, n_t1};
+
+      // S_w = Q_w * K^T : 8 k-steps of 16 over D=128; D split into two 64-wide SW128 boxes
+      auto issue_qk = [&](int w, int ks) {
+        const uint64_t a0 = make_smem_desc(smem_u32(sQ + w * kTileBytes), 16, 1024);
+        const uint64_t b0 = make_smem_desc(smem_u32(sK + ks * kTileBytes), 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < kHeadDim / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
+          umma_ss(tS[w], desc_advance(a0, off), desc_advance(b0, off), idesc_qk, kk > 0 ? 1u : 0u);
+        }
+      };
+      // O_w (+)= P_w * V : 8 k-steps of 16 keys; V tile is [keys][d] -> MN-major B,
+      // LBO = 16 KiB between the two 64-wide d blocks, SBO = 1 KiB between 8-key groups
+      auto issue_pv = [&](int w, int vs, bool acc) {
+        const uint64_t b0 = make_smem_desc(smem_u32(sV + vs * kTileBytes), kBoxBytes, 1024);
+#pragma unroll
+        for (int kk = 0; kk < kBlockN / 16; ++kk) {
+          umma_ts(tO[w], tS[w] + kk * 8, desc_advance(b0, kk * 16 * 128), idesc_pv, (acc || kk > 0) ? 1u : 0u);
+        }
+      };
+
+      if (n_max > 0) {
+        mbar_wait(&bars->q_full, 0);
+        mbar_wait(&bars->k_full[0], 0);
+        tc_fence_after();
+        for (int w = 0; w < 2; ++w) {
+          if (n_t[w] > 0) {
+            issue_qk(w, 0);
+            umma_commit(&bars->s_full[w]);
+          }
+        }
+        umma_commit(&bars->k_empty[0]);
+      }
+      for (int i = 0; i < n_max; ++i) {
+        const int vs = i % kVStages;
+        mbar_wait(&bars->v_full[vs], (i / kVStages) & 1);
+        tc_fence_after();
+        const bool have_next = (i + 1) < n_max;
+        const int ks = (i + 1) % kKStages;
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          if (i < n_t[w]) {
+            mbar_wait(&bars->p_ready[w], i & 1);
+            tc_fence_after();
+            issue_pv(w, vs, (i > 0) || p.load_state);
+            umma_commit(&bars->o_done[w]);
+          }
+          if (w == 1) umma_commit(&bars->v_empty[vs]);
+          if (have_next) {
+            if (w == 0) {
+              mbar_wait(&bars->k_full[ks], ((i + 1) / kKStages) & 1);
+              tc_fence_after();
+            }
+            if (i + 1 < n_t[w]) {
+              issue_qk(w, ks);
+              umma_commit(&bars->s_full[w]);
+            }
+            if (w == 1) umma_commit(&bars->k_empty[ks]);
+          }
+        }
+      }
+    }
+  } else {
+    // ============================================================ softmax warps
+    const int w = warp >> 2;                  // Q tile handled by this warpgroup
+    const int t = threadIdx.x & 127;          // row within the tile == TMEM lane
+    const int r0 = row0 + w * kBlockM;
+    const int n = w == 0 ? n_t0 : n_t1;
+    if (r0 < p.Sq) {
+      const int row = r0 + t;
+      const bool valid_row = row < p.Sq;
+      const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+      const uint32_t tS = tmem_base + lane_base + w * 128;
+      const uint32_t tO = tmem_base + lane_base + 256 + w * 128;
+      const float scale_log2 = p.scale_log2;
+      const int limit = p.causal ? min(row + p.causal_off, p.Sk - 1) : p.Sk - 1;
+      const int tile_min_limit = p.causal ? min(r0 + p.causal_off, p.Sk - 1) : p.Sk - 1;
+
+      float m = -INFINITY, l = 0.f;
+      if (p.load_state) {
+        float lse_prev = -INFINITY;
+        if (valid_row) lse_prev = p.lse[(int64_t)b * p.lse_sb + (int64_t)h * p.lse_sh + row];
+        if (lse_prev != -INFINITY) {
+          m = lse_prev * kLog2e;
+          l = 1.f;
+        }
+        const float* src = p.o_acc + (int64_t)b * p.oacc_sb + (int64_t)row * p.oacc_ss + (int64_t)h * p.oacc_sh;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 f = valid_row ? __ldg(reinterpret_cast<const float4*>(src + c * 32 + j * 4))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[j * 4 + 0] = __float_as_uint(f.x);
+            v[j * 4 + 1] = __float_as_uint(f.y);
+            v[j * 4 + 2] = __float_as_uint(f.z);
+            v[j * 4 + 3] = __float_as_uint(f.w);
+          }
+          tmem_st_x32(tO + c * 32, v);
+        }
+        tmem_wait_st();
+      }
+
+      for (int i = 0; i < n; ++i) {
+        mbar_wait(&bars->s_full[w], i & 1);
+        tc_fence_after();
+        uint32_t sr[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, sr + c * 32);
+        tmem_wait_ld();
+        float* s = reinterpret_cast<float*>(sr);
+
+        const int kbase = i * kBlockN;
+        if (kbase + kBlockN - 1 > tile_min_limit) {  // warpgroup-uniform
+#pragma unroll
+          for (int c = 0; c < 128; ++c)
+            if (kbase + c > limit) s[c] = -INFINITY;
+        }
+        float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+        for (int c = 4; c < 128; c += 4) {
+          mx0 = fmaxf(mx0, s[c]);
+          mx1 = fmaxf(mx1, s[c + 1]);
+          mx2 = fmaxf(mx2, s[c + 2]);
+          mx3 = fmaxf(mx3, s[c + 3]);
+        }
+        const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2);
+        const bool grow = m_new > m + kRescaleThreshold;  // also true for m == -inf, m_new finite
+        if (__any_sync(0xffffffffu, grow)) {
+          const bool o_live = (i > 0) || p.load_state;
+          if (o_live) {
+            if (i > 0) {
+              mbar_wait(&bars->o_done[w], (i - 1) & 1);
+              tc_fence_after();
+            }
+            const float f = (m == -INFINITY) ? 0.f : ex2(m - m_new);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t v[32];
+              tmem_ld_x32(tO + c * 32, v);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * f);
+              tmem_st_x32(tO + c * 32, v);
+            }
+            l *= f;
+          }
+          m = m_new;
+        }
+        const float neg_m = (m == -INFINITY) ? 0.f : -m;
+        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 128; c += 4) {
+          s[c] = ex2(fmaf(s[c], scale_log2, neg_m));
+          s[c + 1] = ex2(fmaf(s[c + 1], scale_log2, neg_m));
+          s[c + 2] = ex2(fmaf(s[c + 2], scale_log2, neg_m));
+          s[c + 3] = ex2(fmaf(s[c + 3], scale_log2, neg_m));
+          sum0 += s[c];
+          sum1 += s[c + 1];
+          sum2 += s[c + 2];
+          sum3 += s[c + 3];
+        }
+        l += (sum0 + sum1) + (sum2 + sum3);
+        // pack P to 16-bit pairs (element 2c in the low half) and store into S_w cols [0,64)
+#pragma unroll
+        for (int c = 0; c < 64; ++c) sr[c] = pack2<kBF16>(s[2 * c], s[2 * c + 1]);
+        tmem_st_x32(tS, sr);
+        tmem_st_x32(tS + 32, sr + 32);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->p_ready[w]);
+      }
+
+      // ---------------------------------------------------------- epilogue
+      if (n > 0) {
+        mbar_wait(&bars->o_done[w], (n - 1) & 1);
+        tc_fence_after();
+      }
+      const bool o_live = (n > 0) || p.load_state;
+      const float inv_l = l > 0.f ? 1.f / l : 0.f;
+      const float lse_out = l > 0.f ? (m + lg2(l)) * kLn2 : -INFINITY;
+      if (valid_row) p.lse[(int64_t)b * p.lse_sb + (int64_t)h * p.lse_sh + row] = lse_out;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        if (o_live) {
+          tmem_ld_x32(tO + c * 32, v);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        if (valid_row) {
+          if (p.store_lowp) {
+            uint16_t* dst = reinterpret_cast<uint16_t*>(p.o_out) + (int64_t)b * p.oout_sb +
+                            (int64_t)row * p.oout_ss + (int64_t)h * p.oout_sh + c * 32;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack2<kBF16>(__uint_as_float(v[j * 8 + 0]) * inv_l, __uint_as_float(v[j * 8 + 1]) * inv_l);
+              o.y = pack2<kBF16>(__uint_as_float(v[j * 8 + 2]) * inv_l, __uint_as_float(v[j * 8 + 3]) * inv_l);
+              o.z = pack2<kBF16>(__uint_as_float(v[j * 8 + 4]) * inv_l, __uint_as_float(v[j * 8 + 5]) * inv_l);
+              o.w = pack2<kBF16>(__uint_as_float(v[j * 8 + 6]) * inv_l, __uint_as_float(v[j * 8 + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(dst + j * 8) = o;
+            }
+          } else {
+            float* dst = p.o_acc + (int64_t)b * p.oacc_sb + (int64_t)row * p.oacc_ss + (int64_t)h * p.oacc_sh +
+                         c * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 o;
+              o.x = __uint_as_float(v[j * 4 + 0]) * inv_l;
+              o.y = __uint_as_float(v[j * 4 + 1]) * inv_l;
+              o.z = __uint_as_float(v[j * 4 + 2]) * inv_l;
+              o.w = __uint_as_float(v[j * 4 + 3]) * inv_l;
+              *reinterpret_cast<float4*>(dst + j * 4) = o;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+template <bool kBF16>
+static int launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const FwdParams& p,
+                      cudaStream_t stream) {
+  auto kern = fwd_chunk_kernel<kBF16>;
+  static bool configured = false;  // per template instance
+  if (!configured) {
+    BA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+    configured = true;
+  }
+  dim3 grid((p.Sq + 2 * kBlockM - 1) / (2 * kBlockM), p.H, p.B);
+  kern<<<grid, kFwdThreads, kFwdSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+  BA_CHECK_CUDA(cudaGetLastError());
+  return BA_OK;
+}
+
+}  // namespace ba
+
+extern "C" int ba_fwd_chunk(ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_tensor4 o_acc, ba_rowstat lse,
+                            ba_tensor4 o_out, int B, int Sq, int Sk, int H, int D, float scale, int mask_mode,
+                            int causal_offset, int flags, int dtype, void* stream) {
+  using namespace ba;
+  BA_REQUIRE(D == kHeadDim, "ba_fwd_chunk: head dim %d unsupported (only 128)", D);
+  BA_REQUIRE(B > 0 && Sq > 0 && Sk > 0 && H > 0, "ba_fwd_chunk: empty problem B=%d Sq=%d Sk=%d H=%d", B, Sq, Sk, H);
+  BA_REQUIRE(dtype == BA_DTYPE_FP16 || dtype == BA_DTYPE_BF16, "ba_fwd_chunk: bad dtype %d", dtype);
+  BA_REQUIRE(mask_mode == BA_MASK_NONE || mask_mode == BA_MASK_CAUSAL, "ba_fwd_chunk: bad mask mode %d", mask_mode);
+  BA_REQUIRE(scale > 0.f && isfinite(scale), "ba_fwd_chunk: softmax scale must be positive and finite");
+  BA_REQUIRE(q.ptr && k.ptr && v.ptr && lse.ptr, "ba_fwd_chunk: null q/k/v/lse");
+  const bool first = flags & BA_FWD_FIRST, last = flags & BA_FWD_LAST;
+  BA_REQUIRE(!last || o_out.ptr, "ba_fwd_chunk: BA_FWD_LAST needs o_out");
+  BA_REQUIRE((first && last) || o_acc.ptr, "ba_fwd_chunk: fp32 state o_acc required unless FIRST|LAST");
+  BA_REQUIRE(H <= 65535 && B <= 65535, "ba_fwd_chunk: H and B must be <= 65535");
+  if (o_acc.ptr)
+    BA_REQUIRE((reinterpret_cast<uintptr_t>(o_acc.ptr) & 15) == 0 && o_acc.stride_s % 4 == 0 &&
+                   o_acc.stride_h % 4 == 0 && o_acc.stride_b % 4 == 0,
+               "ba_fwd_chunk: o_acc must be 16-byte aligned with strides multiple of 4 elements");
+  if (o_out.ptr)
+    BA_REQUIRE((reinterpret_cast<uintptr_t>(o_out.ptr) & 15) == 0 && o_out.stride_s % 8 == 0 &&
+                   o_out.stride_h % 8 == 0 && o_out.stride_b % 8 == 0,
+               "ba_fwd_chunk: o_out must be 16-byte aligned with strides multiple of 8 elements");
+
+  CUtensorMap tmQ, tmK, tmV;
+  const CUtensorMapDataType dt = lowp_dtype(dtype);
+  int rc;
+  if ((rc = make_tensor_map(&tmQ, q, B, Sq, H, D, dt, 2, 64, kBlockM, true))) return rc;
+  if ((rc = make_tensor_map(&tmK, k, B, Sk, H, D, dt, 2, 64, kBlockN, true))) return rc;
+  if ((rc = make_tensor_map(&tmV, v, B, Sk, H, D, dt, 2, 64, kBlockN, true))) return rc;
+
+  FwdParams p;
+  p.o_acc = static_cast<float*>(o_acc.ptr);
+  p.oacc_sb = o_acc.stride_b, p.oacc_ss = o_acc.stride_s, p.oacc_sh = o_acc.stride_h;
+  p.lse = lse.ptr;
+  p.lse_sb = lse.stride_b, p.lse_sh = lse.stride_h;
+  p.o_out = o_out.ptr;
+  p.oout_sb = o_out.stride_b, p.oout_ss = o_out.stride_s, p.oout_sh = o_out.stride_h;
+  p.B = B, p.Sq = Sq, p.Sk = Sk, p.H = H;
+  p.scale_log2 = scale * kLog2e;
+  p.causal = mask_mode == BA_MASK_CAUSAL;
+  p.causal_off = causal_offset;
+  p.load_state = first ? 0 : 1;
+  p.store_lowp = last ? 1 : 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return dtype == BA_DTYPE_BF16 ? launch_fwd<true>(tmQ, tmK, tmV, p, st) : launch_fwd<false>(tmQ, tmK, tmV, p, st);
+}

@@ -1,0 +1,136 @@
+// Self tests of the sm_100a building blocks used by the attention kernels
+// (called from tests/ only, through ba_selftest): they isolate the TMA box /
+// swizzle layout, the K-major and MN-major shared-memory descriptors, the
+// instruction descriptor, the TMEM load/store lane mapping and the TS-form MMA,
+// so a failing attention parity test can be traced to one assumption.
+#include "host_common.h"
+#include "sm100_ptx.cuh"
+
+namespace ba {
+
+constexpr int kStTile = 128 * 128 * 2;  // 32 KiB
+constexpr int kStBox = kStTile / 2;
+constexpr int kStSmem = 2 * kStTile + 1024 + 64;
+
+// mode 0: out = A * B^T (SS, both K-major)      mode 1: out = A(as P in TMEM) * B (TS, B MN-major)
+// mode 3: out = A^T * B (SS, A MN-major [k][m], B MN-major [k][n])   -- used by the backward
+// mode 2: raw dump of the first TMA box of A
+template <bool kBF16>
+__global__ void __launch_bounds__(128, 1)
+selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const uint16_t* __restrict__ a_raw, void* __restrict__ out, int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStTile;
+  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sB + kStTile);
+  uint64_t* bar_mma = bar_load + 1;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bar_load + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_init(bar_load, 1);
+      mbar_init(bar_mma, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_holder, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+
+  if (t == 0) {
+    mbar_arrive_expect_tx(bar_load, 2 * kStTile);
+    for (int half = 0; half < 2; ++half) {
+      tma_load_4d(sA + half * kStBox, &tmA, bar_load, half * 64, 0, 0, 0);
+      tma_load_4d(sB + half * kStBox, &tmB, bar_load, half * 64, 0, 0, 0);
+    }
+  }
+  mbar_wait(bar_load, 0);
+
+  if (mode == 2) {
+    const uint16_t* s16 = reinterpret_cast<const uint16_t*>(sA);
+    uint16_t* o16 = static_cast<uint16_t*>(out);
+    for (int i = t; i < kStBox / 2; i += 128) o16[i] = s16[i];
+  } else {
+    if (mode == 1) {
+      // thread t stages row t of P into TMEM cols [128, 192) as packed 16-bit pairs
+      uint32_t v[64];
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(a_raw + t * 128);
+#pragma unroll
+      for (int c = 0; c < 64; ++c) v[c] = src[c];
+      tmem_st_x32(tmem_base + lane_base + 128, v);
+      tmem_st_x32(tmem_base + lane_base + 128 + 32, v + 32);
+      tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (t == 0) {
+      if (mode == 0) {
+        constexpr uint32_t idesc = make_idesc(kBF16, 128, 128, false, false);
+        const uint64_t a0 = make_smem_desc(smem_u32(sA), 16, 1024);
+        const uint64_t b0 = make_smem_desc(smem_u32(sB), 16, 1024);
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * kStBox + (kk & 3) * 32;
+          umma_ss(tmem_base, desc_advance(a0, off), desc_advance(b0, off), idesc, kk > 0);
+        }
+      } else if (mode == 1) {
+        constexpr uint32_t idesc = make_idesc(kBF16, 128, 128, false, true);
+        const uint64_t b0 = make_smem_desc(smem_u32(sB), kStBox, 1024);
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ts(tmem_base, tmem_base + 128 + kk * 8, desc_advance(b0, kk * 2048), idesc, kk > 0);
+      } else {  // mode 3: both operands MN-major: A stored [k][m], B stored [k][n]
+        constexpr uint32_t idesc = make_idesc(kBF16, 128, 128, true, true);
+        const uint64_t a0 = make_smem_desc(smem_u32(sA), kStBox, 1024);
+        const uint64_t b0 = make_smem_desc(smem_u32(sB), kStBox, 1024);
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tmem_base, desc_advance(a0, kk * 2048), desc_advance(b0, kk * 2048), idesc, kk > 0);
+      }
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, 0);
+    tc_fence_after();
+    float* o = static_cast<float*>(out) + t * 128;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld_x32(tmem_base + lane_base + c * 32, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[c * 32 + j] = __uint_as_float(v[j]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace ba
+
+extern "C" int ba_selftest(int mode, const void* a, const void* b, void* out, int dtype, void* stream) {
+  using namespace ba;
+  BA_REQUIRE(mode >= 0 && mode <= 3, "ba_selftest: bad mode %d", mode);
+  BA_REQUIRE(a && b && out, "ba_selftest: null pointer");
+  ba_tensor4 ta{const_cast<void*>(a), 128 * 128, 128, 128};
+  ba_tensor4 tb{const_cast<void*>(b), 128 * 128, 128, 128};
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tensor_map(&tmA, ta, 1, 128, 1, 128, lowp_dtype(dtype), 2, 64, 128, true))) return rc;
+  if ((rc = make_tensor_map(&tmB, tb, 1, 128, 1, 128, lowp_dtype(dtype), 2, 64, 128, true))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == BA_DTYPE_BF16) {
+    BA_CHECK_CUDA(cudaFuncSetAttribute(selftest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStSmem));
+    selftest_kernel<true><<<1, 128, kStSmem, st>>>(tmA, tmB, static_cast<const uint16_t*>(a), out, mode);
+  } else {
+    BA_CHECK_CUDA(cudaFuncSetAttribute(selftest_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStSmem));
+    selftest_kernel<false><<<1, 128, kStSmem, st>>>(tmA, tmB, static_cast<const uint16_t*>(a), out, mode);
+  }
+  BA_CHECK_CUDA(cudaGetLastError());
+  return BA_OK;
+}

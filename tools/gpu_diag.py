@@ -1,0 +1,94 @@
+"""First-contact GPU diagnostic: runs each building-block self test and a few
+forward cases, printing error statistics instead of stopping at the first
+failure.  Output goes to stdout and gpurun_out/diag.log."""
+import os
+import sys
+import traceback
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "burst-attention_b200"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+from gpu_util import err_stats, fwd_chunks, selftest  # noqa: E402
+from oracle import attention_oracle as orc  # noqa: E402
+
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+LOG = open(os.path.join(ROOT, "gpurun_out", "diag.log"), "a")
+
+
+def say(*a):
+    s = " ".join(str(x) for x in a)
+    print(s, flush=True)
+    LOG.write(s + "\n")
+    LOG.flush()
+
+
+def run(name, fn):
+    try:
+        say(f"[{name}]", fn())
+    except Exception as e:  # noqa: BLE001
+        say(f"[{name}] EXC {type(e).__name__}: {e}")
+        say(traceback.format_exc())
+
+
+def main():
+    stage = sys.argv[1] if len(sys.argv) > 1 else "all"
+    say("== stage", stage, torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0))
+    torch.manual_seed(0)
+    a = torch.randn(128, 128, device="cuda").to(torch.bfloat16)
+    b = torch.randn(128, 128, device="cuda").to(torch.bfloat16)
+
+    def t_box():
+        raw = selftest(2, a, b).view(torch.bfloat16).view(128, 8, 8)
+        src = a[:, :64].reshape(128, 8, 8)
+        exp = torch.empty_like(raw)
+        for r in range(128):
+            for c in range(8):
+                exp[r, c ^ (r % 8)] = src[r, c]
+        return dict(equal=bool(torch.equal(raw, exp)), linear_equal=bool(torch.equal(raw, src)))
+    if stage in ("all", "selftest"):
+        run("tma_box", t_box)
+        run("ss_kmajor", lambda: err_stats(selftest(0, a, b), a.float() @ b.float().t()))
+        run("ts_pv", lambda: err_stats(selftest(1, a, b), a.float() @ b.float()))
+        run("ss_mnmajor", lambda: err_stats(selftest(3, a, b), a.float().t() @ b.float()))
+    # variants that would match if an assumption were wrong (diagnosis aid)
+        run("ts_pv_vs_AtB", lambda: err_stats(selftest(1, a, b), a.float().t() @ b.float()))
+        run("ts_pv_vs_ABt", lambda: err_stats(selftest(1, a, b), a.float() @ b.float().t()))
+
+    def fwd_case(B, Sq, Sk, H, causal=False, dtype=torch.bfloat16, nchunks=1):
+        def f():
+            g = torch.Generator(device="cuda").manual_seed(Sq * 7 + Sk)
+            q = torch.randn(B, Sq, H, 128, device="cuda", generator=g).to(dtype)
+            ks = [torch.randn(B, Sk, H, 128, device="cuda", generator=g).to(dtype) for _ in range(nchunks)]
+            vs = [torch.randn(B, Sk, H, 128, device="cuda", generator=g).to(dtype) for _ in range(nchunks)]
+            out, lse = fwd_chunks(q, ks, vs, 128 ** -0.5, causal=causal)
+            o_ref, lse_ref = orc.dense_attention(q.cpu(), torch.cat(ks, 1).cpu(), torch.cat(vs, 1).cpu(), causal=causal)
+            return dict(o=err_stats(out, o_ref), lse=err_stats(lse, lse_ref))
+        return f
+    if stage == "selftest":
+        return
+    run("fwd_128x128", fwd_case(1, 128, 128, 1))
+    run("fwd_256x256", fwd_case(1, 256, 256, 2))
+    run("fwd_256x1024", fwd_case(2, 256, 1024, 2))
+    run("fwd_ragged_200x333", fwd_case(1, 200, 333, 2))
+    run("fwd_causal_512", fwd_case(1, 512, 512, 2, causal=True))
+    run("fwd_fp16_256x512", fwd_case(1, 256, 512, 2, dtype=torch.float16))
+    run("fwd_chain3_256x256", fwd_case(1, 256, 256, 2, nchunks=3))
+
+    def timing():
+        q, k, v = (torch.randn(1, 16384, 32, 128, device="cuda").to(torch.bfloat16) for _ in range(3))
+        fwd_chunks(q, [k], [v], 128 ** -0.5)
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(3):
+            fwd_chunks(q, [k], [v], 128 ** -0.5)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        return dict(ms=ms, tflops=4 * 16384 ** 2 * 32 * 128 / ms / 1e9)
+    run("fwd_timing_S16k_H32", timing)
+
+
+if __name__ == "__main__":
+    main()
