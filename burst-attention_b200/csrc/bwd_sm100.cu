@@ -1,7 +1,478 @@
+// ba_bwd_chunk: one ring round of the backward on sm_100a.
+//
+// Replaces the reference's per-round flash_attn_2_cuda.bwd call
+// (burst_utils.py:180-249; Triton twin lao.py:295-595) AND the three full-tensor
+// "dq += buf; dk += buf; dv += buf" passes of burst_attn_interface.py:379-390:
+// the kernel accumulates straight into fp32 dQ / dK / dV accumulators.
+// delta = rowsum(O*dO) and the final lse are inputs (they travel with the
+// Q-bundle), so O itself is never read here.
+//
+// One CTA owns one 128-key block of the home K/V chunk for one (batch, head)
+// and loops over the 128-row blocks of the visiting Q-bundle:
+//   S^T  = K Q_i^T           (SS; TMEM rows = keys, cols = queries)
+//   dP^T = V dO_i^T          (SS)
+//   P^T  = exp2(S^T*c - lse) , dS^T = P^T o (dP^T - delta)      (8 compute warps, thread = key row)
+//   dV  += P^T dO_i          (TS; P^T 16-bit in TMEM aliasing S^T)
+//   dK  += dS^T Q_i          (SS; dS^T staged once in smem, read K-major)
+//   dQ_i = dS K              (SS; the same smem tile read MN-major) -> TMEM (aliasing dP^T)
+//   dQ_i -> 4 reduce warps -> smem -> cp.reduce.async.bulk.tensor (fp32 add in L2) -> dq_acc
+// TMEM (512 cols): S^T/P^T [0,128)  dP^T/dQ [128,256)  dK [256,384)  dV [384,512).
+// smem: K 32K, V 32K, Q 2x32K, dO 32K, dS 32K, dQ staging 2x16K, row stats 2x1K.
+#include <math.h>
+
 #include "host_common.h"
-extern "C" int ba_bwd_chunk(ba_tensor4 d_o, ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_rowstat delta, ba_rowstat lse,
-                 ba_tensor4 dq_acc, ba_tensor4 dk_acc, ba_tensor4 dv_acc, int B, int Sq, int Sk, int H, int D,
-                 float scale, int mask_mode, int causal_offset, int flags, int dtype, void* stream) {
-  ba::set_error("ba_bwd_chunk: not built yet");
-  return BA_ERR_UNSUPPORTED;
+#include "sm100_ptx.cuh"
+
+namespace ba {
+
+constexpr int kBwdThreads = 448;  // warps 0-7 compute, 8-11 dQ reduce, 12 MMA, 13 load
+constexpr int kTile = 128;
+constexpr int kTileB = kTile * kTile * 2;  // 32 KiB 16-bit tile
+constexpr int kBoxB = kTileB / 2;          // 16 KiB: 128 rows x 64 cols SW128 box
+constexpr int kDqStageB = kTile * 32 * 4;  // 16 KiB: 128 rows x 32 fp32 cols SW128 box
+constexpr float kBwdLog2e = 1.4426950408889634f;
+
+struct BwdParams {
+  const float* lse;
+  int64_t lse_sb, lse_sh;
+  const float* delta;
+  int64_t dl_sb, dl_sh;
+  float* dk_acc;
+  int64_t dk_sb, dk_ss, dk_sh;
+  float* dv_acc;
+  int64_t dv_sb, dv_ss, dv_sh;
+  int B, Sq, Sk, H;
+  float scale, scale_log2;
+  int causal, causal_off;
+};
+
+struct __align__(8) BwdBarriers {
+  uint64_t kv_full;
+  uint64_t q_full[2], q_empty[2], stat_full[2];
+  uint64_t do_full, do_empty;
+  uint64_t s_full, p_ready, dp_full, ds_ready, dq_full, dq_free, dkv_full;
+  uint32_t tmem_base;
+};
+
+// smem carve-up (bytes from the 1 KiB-aligned base)
+constexpr int kOffK = 0;
+constexpr int kOffV = kOffK + kTileB;
+constexpr int kOffQ = kOffV + kTileB;        // 2 stages
+constexpr int kOffDO = kOffQ + 2 * kTileB;   // 1 stage
+constexpr int kOffDS = kOffDO + kTileB;
+constexpr int kOffDQ = kOffDS + kTileB;      // 2 staging boxes
+constexpr int kOffStat = kOffDQ + 2 * kDqStageB;  // [2 stages][lse2 128 | delta 128] fp32
+constexpr int kOffBar = kOffStat + 2 * 2 * kTile * 4;
+constexpr int kBwdSmemBytes = kOffBar + 256;  // no align slack: the dynamic smem base is checked to be 1 KiB aligned
+static_assert(kBwdSmemBytes <= 232448, "backward kernel exceeds 227 KiB of shared memory");
+
+template <bool kBF16>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                 const __grid_constant__ CUtensorMap tmDQ, const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B atoms need a 1 KiB-aligned base
+  uint8_t* sK = smem + kOffK;
+  uint8_t* sV = smem + kOffV;
+  uint8_t* sQ = smem + kOffQ;
+  uint8_t* sDO = smem + kOffDO;
+  uint8_t* sDS = smem + kOffDS;
+  uint8_t* sDQ = smem + kOffDQ;
+  float* sStat = reinterpret_cast<float*>(smem + kOffStat);
+  BwdBarriers* bars = reinterpret_cast<BwdBarriers*>(smem + kOffBar);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int k0 = blockIdx.x * kTile;
+  const int nQ = (p.Sq + kTile - 1) / kTile;
+  // first Q block that can see any key of this block: q >= k0 - off
+  const int i_begin = p.causal ? max(0, k0 - p.causal_off) / kTile : 0;
+  const int n_it = max(0, nQ - i_begin);
+  if (n_it == 0) return;  // nothing visible: dK/dV contributions are zero (uniform exit, no barriers yet)
+
+  if (warp == 13 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQ);
+  }
+  if (warp == 12) {
+    if (lane == 0) {
+      mbar_init(&bars->kv_full, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&bars->q_full[s], 1);
+        mbar_init(&bars->q_empty[s], 1);
+        mbar_init(&bars->stat_full[s], 1);
+      }
+      mbar_init(&bars->do_full, 1);
+      mbar_init(&bars->do_empty, 1);
+      mbar_init(&bars->s_full, 1);
+      mbar_init(&bars->p_ready, 8);   // one elected arrive per compute warp
+      mbar_init(&bars->dp_full, 1);
+      mbar_init(&bars->ds_ready, 8);
+      mbar_init(&bars->dq_full, 1);
+      mbar_init(&bars->dq_free, 4);   // one elected arrive per reduce warp
+      mbar_init(&bars->dkv_full, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&bars->tmem_base, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDK = tmem_base + 256, tDV = tmem_base + 384;
+
+  if (warp == 13) {
+    // ============================================================ loader
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars->kv_full, 2 * kTileB);
+      for (int half = 0; half < 2; ++half) {
+        tma_load_4d(sK + half * kBoxB, &tmK, &bars->kv_full, half * 64, h, k0, b);
+        tma_load_4d(sV + half * kBoxB, &tmV, &bars->kv_full, half * 64, h, k0, b);
+      }
+    }
+    for (int it = 0; it < n_it; ++it) {
+      const int q0 = (i_begin + it) * kTile;
+      const int st = it & 1;
+      mbar_wait(&bars->q_empty[st], ((it >> 1) & 1) ^ 1);
+      // row statistics of this Q block: lse in log2 units (+inf for padding rows -> P = 0), delta
+      float* stat = sStat + st * 2 * kTile;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = lane + 32 * j;
+        const int row = q0 + r;
+        float l2 = INFINITY, dl = 0.f;
+        if (row < p.Sq) {
+          l2 = __ldg(p.lse + (int64_t)b * p.lse_sb + (int64_t)h * p.lse_sh + row) * kBwdLog2e;
+          dl = __ldg(p.delta + (int64_t)b * p.dl_sb + (int64_t)h * p.dl_sh + row);
+          if (l2 == -INFINITY) l2 = INFINITY;  // a row that saw no key at all contributes nothing
+        }
+        stat[r] = l2;
+        stat[kTile + r] = dl;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars->stat_full[st]);
+        mbar_arrive_expect_tx(&bars->q_full[st], kTileB);
+        for (int half = 0; half < 2; ++half)
+          tma_load_4d(sQ + st * kTileB + half * kBoxB, &tmQ, &bars->q_full[st], half * 64, h, q0, b);
+        mbar_wait(&bars->do_empty, (it & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars->do_full, kTileB);
+        for (int half = 0; half < 2; ++half)
+          tma_load_4d(sDO + half * kBoxB, &tmDO, &bars->do_full, half * 64, h, q0, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 12) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t id_kk = make_idesc(kBF16, 128, 128, false, false);  // A K-major, B K-major
+      constexpr uint32_t id_kn = make_idesc(kBF16, 128, 128, false, true);   // A K-major/TMEM, B MN-major
+      constexpr uint32_t id_nn = make_idesc(kBF16, 128, 128, true, true);    // A MN-major, B MN-major
+      const uint64_t dK_k = make_smem_desc(smem_u32(sK), 16, 1024);          // K tile as K-major A
+      const uint64_t dV_k = make_smem_desc(smem_u32(sV), 16, 1024);
+      const uint64_t dK_n = make_smem_desc(smem_u32(sK), kBoxB, 1024);       // K tile as MN-major B
+      const uint64_t dDO_k = make_smem_desc(smem_u32(sDO), 16, 1024);
+      const uint64_t dDO_n = make_smem_desc(smem_u32(sDO), kBoxB, 1024);
+      const uint64_t dDS_k = make_smem_desc(smem_u32(sDS), 16, 1024);        // dS^T [key][q] as K-major A
+      const uint64_t dDS_n = make_smem_desc(smem_u32(sDS), kBoxB, 1024);     // ... as MN-major A (M = q)
+
+      auto kstep_k = [](int kk) -> uint32_t { return (kk >> 2) * kBoxB + (kk & 3) * 32; };  // K-major k-step
+      auto kstep_n = [](int kk) -> uint32_t { return kk * 16 * 128; };                      // MN-major k-step
+
+      auto issue_S = [&](int st) {  // S^T = K Q^T
+        const uint64_t dQ_k = make_smem_desc(smem_u32(sQ + st * kTileB), 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tS, desc_advance(dK_k, kstep_k(kk)), desc_advance(dQ_k, kstep_k(kk)), id_kk, kk > 0);
+      };
+      auto issue_dP = [&]() {  // dP^T = V dO^T
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tDP, desc_advance(dV_k, kstep_k(kk)), desc_advance(dDO_k, kstep_k(kk)), id_kk, kk > 0);
+      };
+      auto issue_dV = [&](bool acc) {  // dV += P^T dO ; P^T cols: q 0..63 at [0,32), q 64..127 at [64,96)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ts(tDV, tS + (kk >> 2) * 64 + (kk & 3) * 8, desc_advance(dDO_n, kstep_n(kk)), id_kn, acc || kk > 0);
+      };
+      auto issue_dK = [&](int st, bool acc) {  // dK += dS^T Q
+        const uint64_t dQ_n = make_smem_desc(smem_u32(sQ + st * kTileB), kBoxB, 1024);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tDK, desc_advance(dDS_k, kstep_k(kk)), desc_advance(dQ_n, kstep_n(kk)), id_kn, acc || kk > 0);
+      };
+      auto issue_dQ = [&]() {  // dQ = dS K
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tDP, desc_advance(dDS_n, kstep_n(kk)), desc_advance(dK_n, kstep_n(kk)), id_nn, kk > 0);
+      };
+
+      mbar_wait(&bars->kv_full, 0);
+      mbar_wait(&bars->q_full[0], 0);
+      tc_fence_after();
+      issue_S(0);
+      umma_commit(&bars->s_full);
+      mbar_wait(&bars->do_full, 0);
+      tc_fence_after();
+      issue_dP();
+      umma_commit(&bars->dp_full);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        const bool have_next = it + 1 < n_it;
+        mbar_wait(&bars->p_ready, it & 1);
+        tc_fence_after();
+        issue_dV(it > 0);
+        umma_commit(&bars->do_empty);
+        if (have_next) {
+          mbar_wait(&bars->q_full[st ^ 1], ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_S(st ^ 1);
+          umma_commit(&bars->s_full);
+        }
+        mbar_wait(&bars->ds_ready, it & 1);
+        tc_fence_after();
+        issue_dK(st, it > 0);
+        umma_commit(&bars->q_empty[st]);
+        issue_dQ();
+        umma_commit(&bars->dq_full);
+        if (have_next) {
+          mbar_wait(&bars->do_full, (it + 1) & 1);
+          mbar_wait(&bars->dq_free, it & 1);
+          tc_fence_after();
+          issue_dP();
+          umma_commit(&bars->dp_full);
+        }
+      }
+      umma_commit(&bars->dkv_full);
+    }
+  } else if (warp >= 8) {
+    // ============================================================ dQ reduce warps (thread = q row)
+    const int t = threadIdx.x - 256;  // 0..127 == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const bool issuer = (t == 0);
+    for (int it = 0; it < n_it; ++it) {
+      const int q0 = (i_begin + it) * kTile;
+      mbar_wait(&bars->dq_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32(tDP + lane_base + c * 32, v);
+        tmem_wait_ld();
+        if (c == 3) {  // TMEM fully drained: the MMA warp may overwrite it with the next dP^T
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->dq_free);
+        }
+        uint8_t* stage = sDQ + (c & 1) * kDqStageB;
+        if (issuer) tma_store_wait_read<1>();  // the reduce that last read this staging box has finished
+        named_bar_sync(1, 128);
+        // row t: 8 x 16-byte chunks, chunk j stored at position j ^ (t % 8)  (SWIZZLE_128B)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o;
+          o.x = __uint_as_float(v[j * 4 + 0]) * p.scale;
+          o.y = __uint_as_float(v[j * 4 + 1]) * p.scale;
+          o.z = __uint_as_float(v[j * 4 + 2]) * p.scale;
+          o.w = __uint_as_float(v[j * 4 + 3]) * p.scale;
+          *reinterpret_cast<float4*>(stage + t * 128 + ((j ^ (t & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (issuer) {
+          tma_reduce_add_4d(&tmDQ, stage, c * 32, h, q0, b);
+          tma_store_commit();
+        }
+      }
+    }
+    if (issuer) tma_store_wait<0>();
+  } else {
+    // ============================================================ compute warps (thread = key row, half the q cols)
+    const int r = (warp & 3) * 32 + lane;  // key row within the block == TMEM lane
+    const int hf = warp >> 2;              // which 64 query columns
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int key = k0 + r;
+    const bool key_valid = key < p.Sk;
+    const float scale_log2 = p.scale_log2;
+    uint8_t* ds_row = sDS + hf * kBoxB + r * 128;
+    for (int it = 0; it < n_it; ++it) {
+      const int q0 = (i_begin + it) * kTile;
+      const int st = it & 1;
+      const float* stat = sStat + st * 2 * kTile + hf * 64;
+      mbar_wait(&bars->stat_full[st], (it >> 1) & 1);
+      mbar_wait(&bars->s_full, it & 1);
+      tc_fence_after();
+      float pr[64];
+      {
+        uint32_t* sr = reinterpret_cast<uint32_t*>(pr);
+        tmem_ld_x32(tS + lane_base + hf * 64, sr);
+        tmem_ld_x32(tS + lane_base + hf * 64 + 32, sr + 32);
+        tmem_wait_ld();
+      }
+      // visible iff key <= q + off  <=>  q >= key - off ; whole block visible when q0 + off >= k0 + 127
+      const bool need_mask = p.causal && (q0 + p.causal_off < k0 + kTile - 1);
+      const int qmin = key - p.causal_off - q0 - hf * 64;  // first visible column index (local to this half)
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) {
+        const float4 l2 = *reinterpret_cast<const float4*>(stat + c4 * 4);
+        pr[c4 * 4 + 0] = ex2(fmaf(pr[c4 * 4 + 0], scale_log2, -l2.x));
+        pr[c4 * 4 + 1] = ex2(fmaf(pr[c4 * 4 + 1], scale_log2, -l2.y));
+        pr[c4 * 4 + 2] = ex2(fmaf(pr[c4 * 4 + 2], scale_log2, -l2.z));
+        pr[c4 * 4 + 3] = ex2(fmaf(pr[c4 * 4 + 3], scale_log2, -l2.w));
+      }
+      if (!key_valid) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) pr[c] = 0.f;
+      } else if (need_mask) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (c < qmin) pr[c] = 0.f;
+      }
+      {
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) pk[c] = pack2<kBF16>(pr[2 * c], pr[2 * c + 1]);
+        tmem_st_x32(tS + lane_base + hf * 64, pk);  // P^T for this half aliases its own S^T columns
+        tmem_wait_st();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p_ready);
+
+      // dS^T = P^T o (dP^T - delta)
+      mbar_wait(&bars->dp_full, it & 1);
+      tc_fence_after();
+      if (it > 0) mbar_wait(&bars->dq_full, (it - 1) & 1);  // dK(it-1), dQ(it-1) finished reading sDS
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t dp[32];
+        tmem_ld_x32(tDP + lane_base + hf * 64 + half * 32, dp);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 dl = *reinterpret_cast<const float4*>(stat + kTile + half * 32 + c4 * 4);
+          const int c = half * 32 + c4 * 4;
+          const float d0 = pr[c + 0] * (__uint_as_float(dp[c4 * 4 + 0]) - dl.x);
+          const float d1 = pr[c + 1] * (__uint_as_float(dp[c4 * 4 + 1]) - dl.y);
+          const float d2 = pr[c + 2] * (__uint_as_float(dp[c4 * 4 + 2]) - dl.z);
+          const float d3 = pr[c + 3] * (__uint_as_float(dp[c4 * 4 + 3]) - dl.w);
+          dp[c4 * 2 + 0] = pack2<kBF16>(d0, d1);  // in-place: slot 2*c4 <= 4*c4 already consumed
+          dp[c4 * 2 + 1] = pack2<kBF16>(d2, d3);
+        }
+        // 32 columns = 64 bytes = 4 x 16-byte chunks (chunk index within the 128-byte row: half*4 + j)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o = make_uint4(dp[j * 4 + 0], dp[j * 4 + 1], dp[j * 4 + 2], dp[j * 4 + 3]);
+          *reinterpret_cast<uint4*>(ds_row + (((half * 4 + j) ^ (r & 7)) << 4)) = o;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->ds_ready);
+    }
+
+    // ---------------------------------------------------------- epilogue: dk_acc += scale*dK, dv_acc += dV
+    mbar_wait(&bars->dkv_full, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      float* base = which == 0 ? p.dk_acc : p.dv_acc;
+      const int64_t sb = which == 0 ? p.dk_sb : p.dv_sb, ss = which == 0 ? p.dk_ss : p.dv_ss,
+                    sh = which == 0 ? p.dk_sh : p.dv_sh;
+      const float mul = which == 0 ? p.scale : 1.f;
+      float* dst = base + (int64_t)b * sb + (int64_t)key * ss + (int64_t)h * sh + hf * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_x32((which == 0 ? tDK : tDV) + lane_base + hf * 64 + c * 32, v);
+        tmem_wait_ld();
+        if (key_valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4* ptr = reinterpret_cast<float4*>(dst + c * 32 + j * 4);
+            float4 a = *ptr;
+            a.x = fmaf(__uint_as_float(v[j * 4 + 0]), mul, a.x);
+            a.y = fmaf(__uint_as_float(v[j * 4 + 1]), mul, a.y);
+            a.z = fmaf(__uint_as_float(v[j * 4 + 2]), mul, a.z);
+            a.w = fmaf(__uint_as_float(v[j * 4 + 3]), mul, a.w);
+            *ptr = a;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) tmem_dealloc(tmem_base, 512);
+}
+
+template <bool kBF16>
+static int launch_bwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                      const CUtensorMap& tmDO, const CUtensorMap& tmDQ, const BwdParams& p, cudaStream_t stream) {
+  auto kern = bwd_chunk_kernel<kBF16>;
+  BA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes));
+  dim3 grid((p.Sk + kTile - 1) / kTile, p.H, p.B);
+  kern<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(tmQ, tmK, tmV, tmDO, tmDQ, p);
+  BA_CHECK_CUDA(cudaGetLastError());
+  return BA_OK;
+}
+
+static bool f32_view_ok(const ba_tensor4& t) {
+  return t.ptr && (reinterpret_cast<uintptr_t>(t.ptr) & 15) == 0 && t.stride_b % 4 == 0 && t.stride_s % 4 == 0 &&
+         t.stride_h % 4 == 0;
+}
+
+}  // namespace ba
+
+extern "C" int ba_bwd_chunk(ba_tensor4 d_o, ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_rowstat delta,
+                            ba_rowstat lse, ba_tensor4 dq_acc, ba_tensor4 dk_acc, ba_tensor4 dv_acc, int B, int Sq,
+                            int Sk, int H, int D, float scale, int mask_mode, int causal_offset, int flags, int dtype,
+                            void* stream) {
+  using namespace ba;
+  BA_REQUIRE(D == kTile, "ba_bwd_chunk: head dim %d unsupported (only 128)", D);
+  BA_REQUIRE(B > 0 && Sq > 0 && Sk > 0 && H > 0, "ba_bwd_chunk: empty problem B=%d Sq=%d Sk=%d H=%d", B, Sq, Sk, H);
+  BA_REQUIRE(dtype == BA_DTYPE_FP16 || dtype == BA_DTYPE_BF16, "ba_bwd_chunk: bad dtype %d", dtype);
+  BA_REQUIRE(mask_mode == BA_MASK_NONE || mask_mode == BA_MASK_CAUSAL, "ba_bwd_chunk: bad mask mode %d", mask_mode);
+  BA_REQUIRE(scale > 0.f && isfinite(scale), "ba_bwd_chunk: softmax scale must be positive and finite");
+  BA_REQUIRE(d_o.ptr && q.ptr && k.ptr && v.ptr && delta.ptr && lse.ptr, "ba_bwd_chunk: null input");
+  BA_REQUIRE(f32_view_ok(dq_acc) && f32_view_ok(dk_acc) && f32_view_ok(dv_acc),
+             "ba_bwd_chunk: fp32 accumulators must be non-null, 16-byte aligned, strides multiple of 4");
+  BA_REQUIRE(H <= 65535 && B <= 65535, "ba_bwd_chunk: H and B must be <= 65535");
+  (void)flags;  // BA_BWD_DETERMINISTIC: dQ is reduced with fp32 adds in L2 (order not fixed) -- see DESIGN.md
+
+  CUtensorMap tmQ, tmK, tmV, tmDO, tmDQ;
+  const CUtensorMapDataType dt = lowp_dtype(dtype);
+  int rc;
+  if ((rc = make_tensor_map(&tmQ, q, B, Sq, H, D, dt, 2, 64, kTile, true))) return rc;
+  if ((rc = make_tensor_map(&tmDO, d_o, B, Sq, H, D, dt, 2, 64, kTile, true))) return rc;
+  if ((rc = make_tensor_map(&tmK, k, B, Sk, H, D, dt, 2, 64, kTile, true))) return rc;
+  if ((rc = make_tensor_map(&tmV, v, B, Sk, H, D, dt, 2, 64, kTile, true))) return rc;
+  if ((rc = make_tensor_map(&tmDQ, dq_acc, B, Sq, H, D, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 32, kTile, true)))
+    return rc;
+
+  BwdParams p;
+  p.lse = lse.ptr, p.lse_sb = lse.stride_b, p.lse_sh = lse.stride_h;
+  p.delta = delta.ptr, p.dl_sb = delta.stride_b, p.dl_sh = delta.stride_h;
+  p.dk_acc = static_cast<float*>(dk_acc.ptr);
+  p.dk_sb = dk_acc.stride_b, p.dk_ss = dk_acc.stride_s, p.dk_sh = dk_acc.stride_h;
+  p.dv_acc = static_cast<float*>(dv_acc.ptr);
+  p.dv_sb = dv_acc.stride_b, p.dv_ss = dv_acc.stride_s, p.dv_sh = dv_acc.stride_h;
+  p.B = B, p.Sq = Sq, p.Sk = Sk, p.H = H;
+  p.scale = scale;
+  p.scale_log2 = scale * kBwdLog2e;
+  p.causal = mask_mode == BA_MASK_CAUSAL;
+  p.causal_off = causal_offset;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return dtype == BA_DTYPE_BF16 ? launch_bwd<true>(tmQ, tmK, tmV, tmDO, tmDQ, p, st)
+                                : launch_bwd<false>(tmQ, tmK, tmV, tmDO, tmDQ, p, st);
 }

@@ -1,0 +1,49 @@
+"""Public API (burst_attn_func / burst_attn_func_striped) on one GPU (W=1),
+through autograd, against the oracle -- the reference's own test protocol
+(test/test_burst.py:159-219: b=2, s=256*W, n=32, d=128, fp16, rtol=1e-3/atol=1e-2)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from burst_attn import burst_attn_func, burst_attn_func_striped  # noqa: E402
+from gpu_util import TOL  # noqa: E402
+from oracle import attention_oracle as orc  # noqa: E402
+
+
+@pytest.mark.parametrize("func", [burst_attn_func, burst_attn_func_striped])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_reference_protocol_w1(func, causal, dtype):
+    torch.manual_seed(0)
+    b, s, n, d = 2, 256, 32, 128
+    q, k, v, do = (torch.randn(b, s, n, d, device="cuda", dtype=dtype) for _ in range(4))
+    qq, kk, vv = (t.clone().requires_grad_() for t in (q, k, v))
+    o = func(qq, kk, vv, None, "cuda", causal, True, False, None)
+    dq, dk, dv = torch.autograd.grad(o, (qq, kk, vv), do)
+    o_ref, _, dq_ref, dk_ref, dv_ref = orc.dense_attention_bwd(q.cpu(), k.cpu(), v.cpu(), do.cpu(), None, causal)
+    assert o.dtype == dtype and dq.dtype == dtype
+    # gradients of a 16-bit O: the oracle differentiates the exact O, allow the dtype's tolerance
+    torch.testing.assert_close(o.double().cpu(), o_ref, **TOL[dtype])
+    for g, r in ((dv, dv_ref), (dk, dk_ref), (dq, dq_ref)):
+        torch.testing.assert_close(g.double().cpu(), r, **TOL[torch.bfloat16] if dtype == torch.bfloat16 else
+                                   dict(rtol=1e-3, atol=1e-2))
+
+
+def test_normal_layout_flash_none():
+    torch.manual_seed(1)
+    q, k, v, do = (torch.randn(1, 4, 384, 128, device="cuda", dtype=torch.bfloat16) for _ in range(4))
+    qq, kk, vv = (t.clone().requires_grad_() for t in (q, k, v))
+    o = burst_attn_func(qq, kk, vv, None, None, False)
+    dq, dk, dv = torch.autograd.grad(o, (qq, kk, vv), do)
+    p = lambda t: t.permute(0, 2, 1, 3).cpu()
+    o_ref, _, dq_ref, dk_ref, dv_ref = orc.dense_attention_bwd(p(q), p(k), p(v), p(do))
+    torch.testing.assert_close(p(o).double(), o_ref, **TOL[torch.bfloat16])
+    for g, r in ((dv, dv_ref), (dk, dk_ref), (dq, dq_ref)):
+        torch.testing.assert_close(p(g).double(), r, **TOL[torch.bfloat16])
+
+
+def test_causal_requires_cuda_flash_like_reference():
+    q = torch.randn(1, 128, 1, 128, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(AssertionError):
+        burst_attn_func(q, q, q, None, "triton", True)

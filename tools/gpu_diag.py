@@ -32,6 +32,44 @@ def run(name, fn):
         say(traceback.format_exc())
 
 
+def bwd_stage():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_gpu_bwd as tb
+
+    def case(B, Sq, Sk, H, causal=False, off=0, dtype=torch.bfloat16):
+        def f():
+            q, do = tb._mk(B, Sq, H, dtype, 1), tb._mk(B, Sq, H, dtype, 2)
+            k, v = tb._mk(B, Sk, H, dtype, 3), tb._mk(B, Sk, H, dtype, 4)
+            got, ref = tb.run_bwd(q, k, v, do, causal, off)
+            return {n: err_stats(g, r) for n, g, r in zip(("delta", "dq", "dk", "dv"), got, ref)}
+        return f
+    run("bwd_128x128", case(1, 128, 128, 1))
+    run("bwd_256x384", case(2, 256, 384, 2))
+    run("bwd_ragged_200x333", case(1, 200, 333, 2))
+    run("bwd_causal_384", case(1, 384, 384, 2, True, 0))
+    run("bwd_strict_384", case(1, 384, 384, 2, True, -1))
+    run("bwd_fp16_256x256", case(1, 256, 256, 2, dtype=torch.float16))
+
+    def timing():
+        from burst_attn.chunk_ops import NativeOps
+        ops = NativeOps()
+        S, H = 16384, 32
+        q, k, v, do = (torch.randn(1, S, H, 128, device="cuda").to(torch.bfloat16) for _ in range(4))
+        lse = torch.full((1, H, S), 9.0, device="cuda")
+        delta = torch.zeros(1, H, S, device="cuda")
+        acc = [torch.zeros(1, S, H, 128, device="cuda") for _ in range(3)]
+        ops.bwd_chunk(do, q, k, v, delta, lse, acc[0], acc[1], acc[2], 128 ** -0.5, False, 0, 1)
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(3):
+            ops.bwd_chunk(do, q, k, v, delta, lse, acc[0], acc[1], acc[2], 128 ** -0.5, False, 0, 1)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        return dict(ms=ms, tflops=2.5 * 4 * S ** 2 * H * 128 / ms / 1e9)
+    run("bwd_timing_S16k_H32", timing)
+
+
 def main():
     stage = sys.argv[1] if len(sys.argv) > 1 else "all"
     say("== stage", stage, torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0))
@@ -68,6 +106,8 @@ def main():
         return f
     if stage == "selftest":
         return
+    if stage == "bwd":
+        return bwd_stage()
     run("fwd_128x128", fwd_case(1, 128, 128, 1))
     run("fwd_256x256", fwd_case(1, 256, 256, 2))
     run("fwd_256x1024", fwd_case(2, 256, 1024, 2))
