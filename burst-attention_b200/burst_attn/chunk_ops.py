@@ -28,18 +28,42 @@ class NativeOps:
     def __init__(self):
         self.lib = _n.lib()  # raises if the library is missing -- no fallback
         self.launches = 0    # kernels launched through this object (bench.py's gpu_launches)
+        self.timing = None   # bench.py: {kernel name: [(start_event, end_event), ...]} when enabled
+
+    def enable_timing(self, on=True):
+        """Bracket every launch with CUDA events on the launching stream (bench.py roofline)."""
+        self.timing = {} if on else None
+
+    def _t0(self, dev):
+        if self.timing is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream(dev))
+        return e
+
+    def _t1(self, name, e0, dev):
+        if e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(torch.cuda.current_stream(dev))
+            self.timing.setdefault(name, []).append((e0, e1))
+
+    def kernel_ms(self):
+        """{kernel name: (launches, total ms)} -- call after a synchronize."""
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (self.timing or {}).items()}
 
     # ---- forward round: fold chunk (k, v) into (o_acc, lse); on last write o_out
     def fwd_chunk(self, q, k, v, o_acc, lse, o_out, scale, causal, causal_offset, first, last, seq_dim):
         B, Sq, H, D = _dims(q, seq_dim)
         Sk = k.shape[seq_dim]
         flags = (_n.BA_FWD_FIRST if first else 0) | (_n.BA_FWD_LAST if last else 0)
+        e0 = self._t0(q.device)
         rc = self.lib.ba_fwd_chunk(
             _n.t4(q, seq_dim), _n.t4(k, seq_dim), _n.t4(v, seq_dim), _n.t4(o_acc, seq_dim), _n.rs(lse),
             _n.t4(o_out, seq_dim), B, Sq, Sk, H, D, float(scale),
             _n.BA_MASK_CAUSAL if causal else _n.BA_MASK_NONE, int(causal_offset), flags,
             _n.dtype_code(q.dtype), _n.stream_ptr(q.device))
         _n.check(rc, "ba_fwd_chunk")
+        self._t1("fwd_chunk_kernel", e0, q.device)
         self.launches += 1
 
     # ---- delta = rowsum(O * dO)
@@ -55,12 +79,14 @@ class NativeOps:
                   deterministic=False):
         B, Sq, H, D = _dims(q, seq_dim)
         Sk = k.shape[seq_dim]
+        e0 = self._t0(q.device)
         rc = self.lib.ba_bwd_chunk(
             _n.t4(d_o, seq_dim), _n.t4(q, seq_dim), _n.t4(k, seq_dim), _n.t4(v, seq_dim), _n.rs(delta), _n.rs(lse),
             _n.t4(dq_acc, seq_dim), _n.t4(dk_acc, seq_dim), _n.t4(dv_acc, seq_dim), B, Sq, Sk, H, D, float(scale),
             _n.BA_MASK_CAUSAL if causal else _n.BA_MASK_NONE, int(causal_offset), 1 if deterministic else 0,
             _n.dtype_code(q.dtype), _n.stream_ptr(q.device))
         _n.check(rc, "ba_bwd_chunk")
+        self._t1("bwd_chunk_kernel", e0, q.device)
         self.launches += 1
 
     # ---- dst (16-bit) = src (fp32)
