@@ -25,12 +25,21 @@
 
 namespace ba {
 
-constexpr int kBwdThreads = 448;  // warps 0-7 compute, 8-11 dQ reduce, 12 MMA, 13 load
+constexpr int kBwdThreads = 512;  // warps 0-7 compute, 8-11 dQ reduce, 12 MMA, 13 load, 14-15 idle (register donors)
 constexpr int kTile = 128;
 constexpr int kTileB = kTile * kTile * 2;  // 32 KiB 16-bit tile
 constexpr int kBoxB = kTileB / 2;          // 16 KiB: 128 rows x 64 cols SW128 box
 constexpr int kDqStageB = kTile * 32 * 4;  // 16 KiB: 128 rows x 32 fp32 cols SW128 box
 constexpr float kBwdLog2e = 1.4426950408889634f;
+
+template <int N>
+__device__ __forceinline__ void reg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 
 struct BwdParams {
   const float* lse;
@@ -129,8 +138,12 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_base = bars->tmem_base;
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDK = tmem_base + 256, tDV = tmem_base + 384;
 
+  // register re-distribution (512 threads x 128 at launch): the MMA/load warpgroup donates to the
+  // dQ-reduce warpgroup, which needs a whole 128-column TMEM row in registers to free TMEM early
+
   if (warp == 13) {
     // ============================================================ loader
+    reg_dec<64>();
     if (lane == 0) {
       mbar_arrive_expect_tx(&bars->kv_full, 2 * kTileB);
       for (int half = 0; half < 2; ++half) {
@@ -172,7 +185,8 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp == 12) {
     // ============================================================ MMA issuer
-    if (lane == 0) {
+    reg_dec<64>();
+    {
       constexpr uint32_t id_kk = make_idesc(kBF16, 128, 128, false, false);  // A K-major, B K-major
       constexpr uint32_t id_kn = make_idesc(kBF16, 128, 128, false, true);   // A K-major/TMEM, B MN-major
       constexpr uint32_t id_nn = make_idesc(kBF16, 128, 128, true, true);    // A MN-major, B MN-major
@@ -253,8 +267,11 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       umma_commit(&bars->dkv_full);
     }
+  } else if (warp >= 12) {
+    reg_dec<64>();  // idle register donors (warps 14, 15)
   } else if (warp >= 8) {
     // ============================================================ dQ reduce warps (thread = q row)
+    reg_inc<160>();
     const int t = threadIdx.x - 256;  // 0..127 == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const bool issuer = (t == 0);
@@ -262,16 +279,17 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int q0 = (i_begin + it) * kTile;
       mbar_wait(&bars->dq_full, it & 1);
       tc_fence_after();
+      // whole dQ row -> registers, then hand the TMEM region straight back to the MMA warp
+      // (the next dP^T is waiting for it); staging to smem / TMA happens from registers
+      uint32_t v[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_x32(tDP + lane_base + c * 32, v + c * 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->dq_free);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_x32(tDP + lane_base + c * 32, v);
-        tmem_wait_ld();
-        if (c == 3) {  // TMEM fully drained: the MMA warp may overwrite it with the next dP^T
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->dq_free);
-        }
         uint8_t* stage = sDQ + (c & 1) * kDqStageB;
         if (issuer) tma_store_wait_read<1>();  // the reduce that last read this staging box has finished
         named_bar_sync(1, 128);
@@ -279,10 +297,10 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 o;
-          o.x = __uint_as_float(v[j * 4 + 0]) * p.scale;
-          o.y = __uint_as_float(v[j * 4 + 1]) * p.scale;
-          o.z = __uint_as_float(v[j * 4 + 2]) * p.scale;
-          o.w = __uint_as_float(v[j * 4 + 3]) * p.scale;
+          o.x = __uint_as_float(v[c * 32 + j * 4 + 0]) * p.scale;
+          o.y = __uint_as_float(v[c * 32 + j * 4 + 1]) * p.scale;
+          o.z = __uint_as_float(v[c * 32 + j * 4 + 2]) * p.scale;
+          o.w = __uint_as_float(v[c * 32 + j * 4 + 3]) * p.scale;
           *reinterpret_cast<float4*>(stage + t * 128 + ((j ^ (t & 7)) << 4)) = o;
         }
         fence_proxy_async_smem();
@@ -296,6 +314,7 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (issuer) tma_store_wait<0>();
   } else {
     // ============================================================ compute warps (thread = key row, half the q cols)
+    reg_inc<144>();
     const int r = (warp & 3) * 32 + lane;  // key row within the block == TMEM lane
     const int hf = warp >> 2;              // which 64 query columns
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;

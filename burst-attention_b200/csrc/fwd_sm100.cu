@@ -14,10 +14,13 @@
 //                 O_w += P_w V_i       (TS, P bf16/fp16 in TMEM aliasing S_w, V MN-major smem)
 //   warps 0-3   softmax for Q tile 0 (thread t owns row t == TMEM lane t)
 //   warps 4-7   softmax for Q tile 1
-// TMEM (512 cols): S0 [0,128)  S1 [128,256)  O0 [256,384)  O1 [384,512); P_w = S_w cols [0,64).
+// TMEM (512 cols): S0 [0,128)  S1 [128,256)  O0 [256,384)  O1 [384,512).  Each S_w is split into two
+// 64-key sub-tile buffers so QK^T for sub-tile j+1 is already in flight / finished while the softmax
+// warps work on sub-tile j (S double buffering); P (16-bit) aliases the first 32 columns of its buffer.
 // The O rescale is lazy (only when a row max grows by more than 2^8), done in
 // place by the softmax warps, so it is off the steady-state critical path.
 #include <math.h>
+#include <stdlib.h>
 
 #include "host_common.h"
 #include "sm100_ptx.cuh"
@@ -55,24 +58,27 @@ struct __align__(8) FwdBarriers {
   uint64_t q_full;
   uint64_t k_full[kKStages], k_empty[kKStages];
   uint64_t v_full[kVStages], v_empty[kVStages];
-  uint64_t s_full[2];   // MMA -> softmax: S_w ready in TMEM
-  uint64_t p_ready[2];  // softmax -> MMA: P_w written (and O_w rescaled)
-  uint64_t o_done[2];   // MMA -> softmax: P_w V accumulated into O_w
+  uint64_t s_full[2][2];   // MMA -> softmax: S_w sub-tile buffer b ready in TMEM
+  uint64_t p_ready[2][2];  // softmax -> MMA: P_w (buffer b) written (and O_w rescaled)
+  uint64_t o_done[2];      // MMA -> softmax: P_w V accumulated into O_w
   uint32_t tmem_base;
 };
 
+constexpr int kSub = 64;  // keys per softmax sub-tile (S is double-buffered per Q tile in 64-column halves)
 constexpr int kFwdSmemBytes = 2 * kTileBytes + kKStages * kTileBytes + kVStages * kTileBytes + 1024 /*align*/ +
                               256 /*barriers*/;
 
-// number of K tiles a 128-row Q tile starting at r0 must visit
+// number of 64-key sub-tiles a 128-row Q tile starting at r0 must visit
 __device__ __forceinline__ int fwd_trip_count(int r0, const FwdParams& p) {
   if (r0 >= p.Sq) return 0;
   int r_last = min(r0 + kBlockM - 1, p.Sq - 1);
   int max_limit = p.causal ? min(r_last + p.causal_off, p.Sk - 1) : p.Sk - 1;
-  return max_limit < 0 ? 0 : max_limit / kBlockN + 1;
+  return max_limit < 0 ? 0 : max_limit / kSub + 1;
 }
 
-template <bool kBF16>
+// kPoly: every kPoly-th exponential of a row is evaluated with ex2_poly on the FMA pipe instead of
+// MUFU.EX2 (0 = all on MUFU); MUFU (16/clk/SM) is co-critical with the tensor pipe in this kernel.
+template <bool kBF16, int kPoly>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
@@ -87,9 +93,10 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
   const int row0 = blockIdx.x * (2 * kBlockM);
-  const int n_t0 = fwd_trip_count(row0, p);
-  const int n_t1 = fwd_trip_count(row0 + kBlockM, p);
-  const int n_max = max(n_t0, n_t1);
+  const int n_s0 = fwd_trip_count(row0, p);            // sub-tiles for Q tile 0 / 1
+  const int n_s1 = fwd_trip_count(row0 + kBlockM, p);
+  const int n_sub = max(n_s0, n_s1);
+  const int n_tiles = (n_sub + 1) >> 1;                // 128-key K/V tiles to stream
 
   // ---------------------------------------------------------------- setup
   if (warp == 9 && lane == 0) {
@@ -108,10 +115,12 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_init(&bars->v_full[i], 1);
         mbar_init(&bars->v_empty[i], 1);
       }
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&bars->s_full[i], 1);
-        mbar_init(&bars->p_ready[i], 4);  // one elected arrive per softmax warp
-        mbar_init(&bars->o_done[i], 1);
+      for (int w = 0; w < 2; ++w) {
+        for (int bf = 0; bf < 2; ++bf) {
+          mbar_init(&bars->s_full[w][bf], 1);
+          mbar_init(&bars->p_ready[w][bf], 4);  // one elected arrive per softmax warp
+        }
+        mbar_init(&bars->o_done[w], 1);
       }
       fence_mbar_init();
     }
@@ -132,7 +141,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int half = 0; half < 2; ++half)
           tma_load_4d(sQ + w * kTileBytes + half * kBoxBytes, &tmQ, &bars->q_full, half * 64, h,
                       row0 + w * kBlockM, b);
-      for (int i = 0; i < n_max; ++i) {
+      for (int i = 0; i < n_tiles; ++i) {
         const int ks = i % kKStages, kph = (i / kKStages) & 1;
         mbar_wait(&bars->k_empty[ks], kph ^ 1);
         mbar_arrive_expect_tx(&bars->k_full[ks], kTileBytes);
@@ -148,71 +157,78 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
   } else if (warp == 8) {
-    // ============================================================ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc(kBF16, kBlockM, kBlockN, false, false);
+    // ============================================================ MMA issuer (whole warp, elected lane issues)
+    {
+      constexpr uint32_t idesc_qk = make_idesc(kBF16, kBlockM, kSub, false, false);
       constexpr uint32_t idesc_pv = make_idesc(kBF16, kBlockM, kHeadDim, false, true);
-      const uint32_t tS[2] = {tmem_base + 0, tmem_base + 128};
       const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
-      const int n_t[2] = {n_t0, n_t1};
+      const int n_s[2] = {n_s0, n_s1};
 
-      // S_w = Q_w * K^T : 8 k-steps of 16 over D=128; D split into two 64-wide SW128 boxes
-      auto issue_qk = [&](int w, int ks) {
+      // S_w[j&1] = Q_w * K[j]^T for the 64 keys of sub-tile j: 8 k-steps of 16 over D=128
+      // (D split into two 64-wide SW128 boxes); the sub-tile's keys start 64 rows (8 KiB) into each box
+      auto issue_qk = [&](int w, int j) {
+        const int ks = (j >> 1) % kKStages;
         const uint64_t a0 = make_smem_desc(smem_u32(sQ + w * kTileBytes), 16, 1024);
-        const uint64_t b0 = make_smem_desc(smem_u32(sK + ks * kTileBytes), 16, 1024);
+        const uint64_t b0 = make_smem_desc(smem_u32(sK + ks * kTileBytes + (j & 1) * kSub * 128), 16, 1024);
+        const uint32_t tS = tmem_base + w * 128 + (j & 1) * kSub;
 #pragma unroll
         for (int kk = 0; kk < kHeadDim / 16; ++kk) {
           const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
-          umma_ss(tS[w], desc_advance(a0, off), desc_advance(b0, off), idesc_qk, kk > 0 ? 1u : 0u);
+          umma_ss(tS, desc_advance(a0, off), desc_advance(b0, off), idesc_qk, kk > 0 ? 1u : 0u);
         }
       };
-      // O_w (+)= P_w * V : 8 k-steps of 16 keys; V tile is [keys][d] -> MN-major B,
+      // O_w (+)= P_w[j&1] * V[j]: 4 k-steps of 16 keys; V tile is [keys][d] -> MN-major B,
       // LBO = 16 KiB between the two 64-wide d blocks, SBO = 1 KiB between 8-key groups
-      auto issue_pv = [&](int w, int vs, bool acc) {
-        const uint64_t b0 = make_smem_desc(smem_u32(sV + vs * kTileBytes), kBoxBytes, 1024);
+      auto issue_pv = [&](int w, int j, bool acc) {
+        const int vs = (j >> 1) % kVStages;
+        const uint64_t b0 = make_smem_desc(smem_u32(sV + vs * kTileBytes + (j & 1) * kSub * 128), kBoxBytes, 1024);
+        const uint32_t tP = tmem_base + w * 128 + (j & 1) * kSub;
 #pragma unroll
-        for (int kk = 0; kk < kBlockN / 16; ++kk) {
-          umma_ts(tO[w], tS[w] + kk * 8, desc_advance(b0, kk * 16 * 128), idesc_pv, (acc || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < kSub / 16; ++kk) {
+          umma_ts(tO[w], tP + kk * 8, desc_advance(b0, kk * 16 * 128), idesc_pv, (acc || kk > 0) ? 1u : 0u);
         }
       };
 
-      if (n_max > 0) {
+      if (n_sub > 0) {
         mbar_wait(&bars->q_full, 0);
         mbar_wait(&bars->k_full[0], 0);
         tc_fence_after();
-        for (int w = 0; w < 2; ++w) {
-          if (n_t[w] > 0) {
-            issue_qk(w, 0);
-            umma_commit(&bars->s_full[w]);
-          }
-        }
+        for (int j = 0; j < 2; ++j)
+          for (int w = 0; w < 2; ++w)
+            if (j < n_s[w]) {
+              issue_qk(w, j);
+              umma_commit(&bars->s_full[w][j]);
+            }
         umma_commit(&bars->k_empty[0]);
       }
-      for (int i = 0; i < n_max; ++i) {
-        const int vs = i % kVStages;
-        mbar_wait(&bars->v_full[vs], (i / kVStages) & 1);
-        tc_fence_after();
-        const bool have_next = (i + 1) < n_max;
-        const int ks = (i + 1) % kKStages;
+      for (int j = 0; j < n_sub; ++j) {
+        const int tile = j >> 1, sub = j & 1;
+        const int vs = tile % kVStages;
+        if (sub == 0) {
+          mbar_wait(&bars->v_full[vs], (tile / kVStages) & 1);
+          tc_fence_after();
+        }
+        const bool next_qk = (j + 2) < n_sub;          // sub-tile j+2 lives in K tile (tile + 1)
+        const int ks_next = (tile + 1) % kKStages;
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
-          if (i < n_t[w]) {
-            mbar_wait(&bars->p_ready[w], i & 1);
+          if (j < n_s[w]) {
+            mbar_wait(&bars->p_ready[w][sub], tile & 1);
             tc_fence_after();
-            issue_pv(w, vs, (i > 0) || p.load_state);
+            issue_pv(w, j, (j > 0) || p.load_state);
             umma_commit(&bars->o_done[w]);
           }
-          if (w == 1) umma_commit(&bars->v_empty[vs]);
-          if (have_next) {
-            if (w == 0) {
-              mbar_wait(&bars->k_full[ks], ((i + 1) / kKStages) & 1);
+          if (w == 1 && sub == 1) umma_commit(&bars->v_empty[vs]);
+          if (next_qk) {
+            if (w == 0 && sub == 0) {
+              mbar_wait(&bars->k_full[ks_next], ((tile + 1) / kKStages) & 1);
               tc_fence_after();
             }
-            if (i + 1 < n_t[w]) {
-              issue_qk(w, ks);
-              umma_commit(&bars->s_full[w]);
+            if (j + 2 < n_s[w]) {
+              issue_qk(w, j + 2);
+              umma_commit(&bars->s_full[w][sub]);
             }
-            if (w == 1) umma_commit(&bars->k_empty[ks]);
+            if (w == 1 && sub == 1) umma_commit(&bars->k_empty[ks_next]);
           }
         }
       }
@@ -222,12 +238,12 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int w = warp >> 2;                  // Q tile handled by this warpgroup
     const int t = threadIdx.x & 127;          // row within the tile == TMEM lane
     const int r0 = row0 + w * kBlockM;
-    const int n = w == 0 ? n_t0 : n_t1;
+    const int n = w == 0 ? n_s0 : n_s1;
     if (r0 < p.Sq) {
       const int row = r0 + t;
       const bool valid_row = row < p.Sq;
       const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-      const uint32_t tS = tmem_base + lane_base + w * 128;
+      const uint32_t tSw = tmem_base + lane_base + w * 128;
       const uint32_t tO = tmem_base + lane_base + 256 + w * 128;
       const float scale_log2 = p.scale_log2;
       const int limit = p.causal ? min(row + p.causal_off, p.Sk - 1) : p.Sk - 1;
@@ -259,24 +275,26 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_wait_st();
       }
 
-      for (int i = 0; i < n; ++i) {
-        mbar_wait(&bars->s_full[w], i & 1);
+      for (int j = 0; j < n; ++j) {
+        const int bf = j & 1;
+        const uint32_t tS = tSw + bf * kSub;
+        mbar_wait(&bars->s_full[w][bf], (j >> 1) & 1);
         tc_fence_after();
-        uint32_t sr[128];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, sr + c * 32);
+        uint32_t sr[kSub];
+        tmem_ld_x32(tS, sr);
+        tmem_ld_x32(tS + 32, sr + 32);
         tmem_wait_ld();
         float* s = reinterpret_cast<float*>(sr);
 
-        const int kbase = i * kBlockN;
-        if (kbase + kBlockN - 1 > tile_min_limit) {  // warpgroup-uniform
+        const int kbase = j * kSub;
+        if (kbase + kSub - 1 > tile_min_limit) {  // warpgroup-uniform
 #pragma unroll
-          for (int c = 0; c < 128; ++c)
+          for (int c = 0; c < kSub; ++c)
             if (kbase + c > limit) s[c] = -INFINITY;
         }
         float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
 #pragma unroll
-        for (int c = 4; c < 128; c += 4) {
+        for (int c = 4; c < kSub; c += 4) {
           mx0 = fmaxf(mx0, s[c]);
           mx1 = fmaxf(mx1, s[c + 1]);
           mx2 = fmaxf(mx2, s[c + 2]);
@@ -285,10 +303,10 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2);
         const bool grow = m_new > m + kRescaleThreshold;  // also true for m == -inf, m_new finite
         if (__any_sync(0xffffffffu, grow)) {
-          const bool o_live = (i > 0) || p.load_state;
+          const bool o_live = (j > 0) || p.load_state;
           if (o_live) {
-            if (i > 0) {
-              mbar_wait(&bars->o_done[w], (i - 1) & 1);
+            if (j > 0) {
+              mbar_wait(&bars->o_done[w], (j - 1) & 1);
               tc_fence_after();
             }
             const float f = (m == -INFINITY) ? 0.f : ex2(m - m_new);
@@ -298,7 +316,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               tmem_ld_x32(tO + c * 32, v);
               tmem_wait_ld();
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * f);
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
               tmem_st_x32(tO + c * 32, v);
             }
             l *= f;
@@ -307,27 +325,27 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         const float neg_m = (m == -INFINITY) ? 0.f : -m;
         float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+        uint32_t pk[kSub / 2];
 #pragma unroll
-        for (int c = 0; c < 128; c += 4) {
-          s[c] = ex2(fmaf(s[c], scale_log2, neg_m));
-          s[c + 1] = ex2(fmaf(s[c + 1], scale_log2, neg_m));
-          s[c + 2] = ex2(fmaf(s[c + 2], scale_log2, neg_m));
-          s[c + 3] = ex2(fmaf(s[c + 3], scale_log2, neg_m));
-          sum0 += s[c];
-          sum1 += s[c + 1];
-          sum2 += s[c + 2];
-          sum3 += s[c + 3];
+        for (int c = 0; c < kSub; c += 4) {
+          const float p0 = ex2(fmaf(s[c], scale_log2, neg_m));
+          const float p1 = ex2(fmaf(s[c + 1], scale_log2, neg_m));
+          const float p2 = ex2(fmaf(s[c + 2], scale_log2, neg_m));
+          const float x3 = fmaf(s[c + 3], scale_log2, neg_m);
+          const float p3 = (kPoly > 0 && ((c / 4) % (kPoly / 4 > 0 ? kPoly / 4 : 1)) == 0) ? ex2_poly(x3) : ex2(x3);
+          sum0 += p0;
+          sum1 += p1;
+          sum2 += p2;
+          sum3 += p3;
+          pk[c / 2] = pack2<kBF16>(p0, p1);  // element 2c in the low half
+          pk[c / 2 + 1] = pack2<kBF16>(p2, p3);
         }
         l += (sum0 + sum1) + (sum2 + sum3);
-        // pack P to 16-bit pairs (element 2c in the low half) and store into S_w cols [0,64)
-#pragma unroll
-        for (int c = 0; c < 64; ++c) sr[c] = pack2<kBF16>(s[2 * c], s[2 * c + 1]);
-        tmem_st_x32(tS, sr);
-        tmem_st_x32(tS + 32, sr + 32);
+        tmem_st_x32(tS, pk);  // P aliases the first 32 columns of its S buffer
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->p_ready[w]);
+        if (lane == 0) mbar_arrive(&bars->p_ready[w][bf]);
       }
 
       // ---------------------------------------------------------- epilogue
@@ -347,32 +365,32 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tmem_wait_ld();
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0u;
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
         if (valid_row) {
           if (p.store_lowp) {
             uint16_t* dst = reinterpret_cast<uint16_t*>(p.o_out) + (int64_t)b * p.oout_sb +
                             (int64_t)row * p.oout_ss + (int64_t)h * p.oout_sh + c * 32;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int i = 0; i < 4; ++i) {
               uint4 o;
-              o.x = pack2<kBF16>(__uint_as_float(v[j * 8 + 0]) * inv_l, __uint_as_float(v[j * 8 + 1]) * inv_l);
-              o.y = pack2<kBF16>(__uint_as_float(v[j * 8 + 2]) * inv_l, __uint_as_float(v[j * 8 + 3]) * inv_l);
-              o.z = pack2<kBF16>(__uint_as_float(v[j * 8 + 4]) * inv_l, __uint_as_float(v[j * 8 + 5]) * inv_l);
-              o.w = pack2<kBF16>(__uint_as_float(v[j * 8 + 6]) * inv_l, __uint_as_float(v[j * 8 + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(dst + j * 8) = o;
+              o.x = pack2<kBF16>(__uint_as_float(v[i * 8 + 0]) * inv_l, __uint_as_float(v[i * 8 + 1]) * inv_l);
+              o.y = pack2<kBF16>(__uint_as_float(v[i * 8 + 2]) * inv_l, __uint_as_float(v[i * 8 + 3]) * inv_l);
+              o.z = pack2<kBF16>(__uint_as_float(v[i * 8 + 4]) * inv_l, __uint_as_float(v[i * 8 + 5]) * inv_l);
+              o.w = pack2<kBF16>(__uint_as_float(v[i * 8 + 6]) * inv_l, __uint_as_float(v[i * 8 + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(dst + i * 8) = o;
             }
           } else {
             float* dst = p.o_acc + (int64_t)b * p.oacc_sb + (int64_t)row * p.oacc_ss + (int64_t)h * p.oacc_sh +
                          c * 32;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int i = 0; i < 8; ++i) {
               float4 o;
-              o.x = __uint_as_float(v[j * 4 + 0]) * inv_l;
-              o.y = __uint_as_float(v[j * 4 + 1]) * inv_l;
-              o.z = __uint_as_float(v[j * 4 + 2]) * inv_l;
-              o.w = __uint_as_float(v[j * 4 + 3]) * inv_l;
-              *reinterpret_cast<float4*>(dst + j * 4) = o;
+              o.x = __uint_as_float(v[i * 4 + 0]) * inv_l;
+              o.y = __uint_as_float(v[i * 4 + 1]) * inv_l;
+              o.z = __uint_as_float(v[i * 4 + 2]) * inv_l;
+              o.w = __uint_as_float(v[i * 4 + 3]) * inv_l;
+              *reinterpret_cast<float4*>(dst + i * 4) = o;
             }
           }
         }
@@ -386,15 +404,11 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 8) tmem_dealloc(tmem_base, 512);
 }
 
-template <bool kBF16>
+template <bool kBF16, int kPoly>
 static int launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const FwdParams& p,
                       cudaStream_t stream) {
-  auto kern = fwd_chunk_kernel<kBF16>;
-  static bool configured = false;  // per template instance
-  if (!configured) {
-    BA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
-    configured = true;
-  }
+  auto kern = fwd_chunk_kernel<kBF16, kPoly>;
+  BA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
   dim3 grid((p.Sq + 2 * kBlockM - 1) / (2 * kBlockM), p.H, p.B);
   kern<<<grid, kFwdThreads, kFwdSmemBytes, stream>>>(tmQ, tmK, tmV, p);
   BA_CHECK_CUDA(cudaGetLastError());
@@ -447,5 +461,17 @@ extern "C" int ba_fwd_chunk(ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_tensor4
   p.load_state = first ? 0 : 1;
   p.store_lowp = last ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return dtype == BA_DTYPE_BF16 ? launch_fwd<true>(tmQ, tmK, tmV, p, st) : launch_fwd<false>(tmQ, tmK, tmV, p, st);
+  // BA_FWD_POLY (tuning knob, read once): 0 = all exponentials on MUFU, 4 = every 4th, 8 = every 8th on FMA
+  static const int poly = [] {
+    const char* e = getenv("BA_FWD_POLY");
+    return e ? atoi(e) : 0;
+  }();
+  if (dtype == BA_DTYPE_BF16) {
+    if (poly == 4) return launch_fwd<true, 4>(tmQ, tmK, tmV, p, st);
+    if (poly == 8) return launch_fwd<true, 8>(tmQ, tmK, tmV, p, st);
+    return launch_fwd<true, 0>(tmQ, tmK, tmV, p, st);
+  }
+  if (poly == 4) return launch_fwd<false, 4>(tmQ, tmK, tmV, p, st);
+  if (poly == 8) return launch_fwd<false, 8>(tmQ, tmK, tmV, p, st);
+  return launch_fwd<false, 0>(tmQ, tmK, tmV, p, st);
 }

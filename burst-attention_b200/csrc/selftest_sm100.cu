@@ -71,7 +71,7 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (t == 0) {
+    if (warp == 0) {
       if (mode == 0) {
         constexpr uint32_t idesc = make_idesc(kBF16, 128, 128, false, false);
         const uint64_t a0 = make_smem_desc(smem_u32(sA), 16, 1024);

@@ -32,6 +32,19 @@ BA_DEVICE float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA/ALU pipes (no MUFU): Cody-Waite split with the 1.5*2^23 magic constant,
+// cubic minimax for 2^f on [-0.5, 0.5] (max rel. error 1.5e-4, below 16-bit P precision), exponent
+// spliced in with an integer add.  Valid for x <= ~100; x < -126 (incl. -inf) returns ~1e-38.
+BA_DEVICE float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;
+  const float n = t - 12582912.f;
+  const float f = x - n;
+  float p = fmaf(0.05517167f, f, 0.24261113f);
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.99992806f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 BA_DEVICE float lg2(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -152,7 +165,7 @@ BA_DEVICE void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 // MMA completion -> mbarrier arrive (implies tcgen05.fence::before_thread_sync).
 BA_DEVICE void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+  if (elect_one()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
 }
@@ -240,9 +253,12 @@ __host__ __device__ constexpr uint32_t make_idesc(bool bf16, int M, int N, bool 
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
-// D[tmem] (+)= A[smem] * B[smem]     (single thread issues)
+// The MMA / commit wrappers must be called by a CONVERGED warp with warp-uniform
+// arguments; one elected lane issues.  (Issuing from an `if (lane == 0)` region
+// makes ptxas wrap every UTCHMMA in an ELECT/BRA.U.ANY uniformisation loop.)
+// D[tmem] (+)= A[smem] * B[smem]
 BA_DEVICE void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
+  if (elect_one()) asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
@@ -252,7 +268,7 @@ BA_DEVICE void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32
 }
 // D[tmem] (+)= A[tmem] * B[smem]     (A: 128 lanes x K/2 32-bit columns, 2 x 16-bit per column)
 BA_DEVICE void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
+  if (elect_one()) asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"

@@ -70,6 +70,38 @@ def bwd_stage():
     run("bwd_timing_S16k_H32", timing)
 
 
+def perf_stage():
+    """Kernel-only timings (CUDA events, 2 warm-up + 5 timed launches) at S=32768, H=32, bf16."""
+    from burst_attn.chunk_ops import NativeOps
+    ops = NativeOps()
+    S, H = 32768, 32
+    q, k, v, do = (torch.randn(1, S, H, 128, device="cuda").to(torch.bfloat16) for _ in range(4))
+    out = torch.empty_like(q)
+    lse = torch.empty(1, H, S, device="cuda")
+    delta = torch.zeros(1, H, S, device="cuda")
+    acc = [torch.zeros(1, S, H, 128, device="cuda") for _ in range(3)]
+
+    def t(fn, n=5):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    for causal in (False, True):
+        f = lambda: ops.fwd_chunk(q, k, v, None, lse, out, 128 ** -0.5, causal, 0, True, True, 1)
+        ms = t(f)
+        say(f"[perf fwd causal={causal} poly={os.environ.get('BA_FWD_POLY', '0')}] ms={ms:.3f} "
+            f"tflops={4 * S * S * H * 128 / (2 if causal else 1) / ms / 1e9:.1f}")
+    for causal in (False, True):
+        f = lambda: ops.bwd_chunk(do, q, k, v, delta, lse, acc[0], acc[1], acc[2], 128 ** -0.5, causal, 0, 1)
+        ms = t(f)
+        say(f"[perf bwd causal={causal}] ms={ms:.3f} tflops={10 * S * S * H * 128 / (2 if causal else 1) / ms / 1e9:.1f}")
+
+
 def main():
     stage = sys.argv[1] if len(sys.argv) > 1 else "all"
     say("== stage", stage, torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0))
@@ -108,6 +140,8 @@ def main():
         return
     if stage == "bwd":
         return bwd_stage()
+    if stage == "perf":
+        return perf_stage()
     run("fwd_128x128", fwd_case(1, 128, 128, 1))
     run("fwd_256x256", fwd_case(1, 256, 256, 2))
     run("fwd_256x1024", fwd_case(2, 256, 1024, 2))
