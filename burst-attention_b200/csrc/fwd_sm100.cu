@@ -349,6 +349,9 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
 
       // ---------------------------------------------------------- epilogue
+      // With S double-buffered only PV(n-3) is known complete here (S(n-1) was issued behind it), so a
+      // single parity wait would be ambiguous: wait for completion #(n-1), then #n.
+      if (n > 1) mbar_wait(&bars->o_done[w], (n - 2) & 1);
       if (n > 0) {
         mbar_wait(&bars->o_done[w], (n - 1) & 1);
         tc_fence_after();
