@@ -74,7 +74,7 @@ BA_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps after ~4 s (-> CUDA error surfaced to the
+// Bounded wait: a protocol bug traps after ~30 s (-> CUDA error surfaced to the
 // host) instead of hanging the GPU box.
 BA_DEVICE uint64_t global_ns() {
   uint64_t t;
@@ -93,7 +93,7 @@ BA_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
 #pragma unroll 1
     for (int i = 0; i < 1024; ++i)
       if (mbar_try_wait(bar, parity)) return;
-    if (global_ns() - t0 > 4000000000ull) break;
+    if (global_ns() - t0 > 30000000000ull) break;
   }
   printf("ba: mbarrier watchdog block(%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,
          blockIdx.z, threadIdx.x, smem_u32(bar), parity);
