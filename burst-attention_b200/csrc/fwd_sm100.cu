@@ -60,7 +60,8 @@ struct __align__(8) FwdBarriers {
   uint64_t v_full[kVStages], v_empty[kVStages];
   uint64_t s_full[2][2];   // MMA -> softmax: S_w sub-tile buffer b ready in TMEM
   uint64_t p_ready[2][2];  // softmax -> MMA: P_w (buffer b) written (and O_w rescaled)
-  uint64_t o_done[2];      // MMA -> softmax: P_w V accumulated into O_w
+  uint64_t o_done[2];      // MMA -> softmax: P_w V accumulated into O_w (one completion per sub-tile)
+  uint64_t o_final[2];     // MMA -> softmax: the LAST P_w V of this CTA has completed (single completion)
   uint32_t tmem_base;
 };
 
@@ -121,6 +122,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           mbar_init(&bars->p_ready[w][bf], 4);  // one elected arrive per softmax warp
         }
         mbar_init(&bars->o_done[w], 1);
+        mbar_init(&bars->o_final[w], 1);
       }
       fence_mbar_init();
     }
@@ -217,6 +219,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tc_fence_after();
             issue_pv(w, j, (j > 0) || p.load_state);
             umma_commit(&bars->o_done[w]);
+            if (j == n_s[w] - 1) umma_commit(&bars->o_final[w]);
           }
           if (w == 1 && sub == 1) umma_commit(&bars->v_empty[vs]);
           if (next_qk) {
@@ -349,11 +352,10 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
 
       // ---------------------------------------------------------- epilogue
-      // With S double-buffered only PV(n-3) is known complete here (S(n-1) was issued behind it), so a
-      // single parity wait would be ambiguous: wait for completion #(n-1), then #n.
-      if (n > 1) mbar_wait(&bars->o_done[w], (n - 2) & 1);
+      // A parity wait on o_done would be ambiguous here (with S double-buffered the last two PVs may
+      // both be pending or both be done), so the last PV signals a dedicated single-shot barrier.
       if (n > 0) {
-        mbar_wait(&bars->o_done[w], (n - 1) & 1);
+        mbar_wait(&bars->o_final[w], 0);
         tc_fence_after();
       }
       const bool o_live = (n > 0) || p.load_state;
