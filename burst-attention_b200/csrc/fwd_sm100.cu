@@ -66,8 +66,66 @@ struct __align__(8) FwdBarriers {
 };
 
 constexpr int kSub = 64;  // keys per softmax sub-tile (S is double-buffered per Q tile in 64-column halves)
-constexpr int kFwdSmemBytes = 2 * kTileBytes + kKStages * kTileBytes + kVStages * kTileBytes + 1024 /*align*/ +
-                              256 /*barriers*/;
+static_assert(kKStages == 2 && kVStages == 2, "the unrolled MMA issue loop assumes 2-stage K/V rings");
+constexpr uint32_t kOffQ = 0;
+constexpr uint32_t kOffK = 2 * kTileBytes;
+constexpr uint32_t kOffV = kOffK + kKStages * kTileBytes;
+constexpr uint32_t kOffBars = kOffV + kVStages * kTileBytes;
+constexpr int kFwdSmemBytes = kOffBars + 256 /*barriers*/;
+
+// One step (sub-tile j, with U = j & 3 known at compile time so that every TMEM address, smem
+// descriptor and barrier address below is a constant): PV for both Q tiles on sub-tile j, then the
+// QK^T of sub-tile j+2 into the S buffers that PV just released.  sb16 = (smem base address) >> 4.
+template <bool kBF16, int U>
+__device__ __forceinline__ void fwd_mma_step(int j, uint32_t sb16, FwdBarriers* bars, int n_s0, int n_s1, int n_sub,
+                                             bool load_state) {
+  constexpr int sub = U & 1, st = U >> 1, st_next = st ^ 1;
+  constexpr uint32_t idesc_qk = make_idesc(kBF16, kBlockM, kSub, false, false);
+  constexpr uint32_t idesc_pv = make_idesc(kBF16, kBlockM, kHeadDim, false, true);
+  constexpr uint32_t hi = desc_hi(1024);
+  const int tile = j >> 1;
+  if (sub == 0) {
+    mbar_wait(&bars->v_full[st], (tile >> 1) & 1);
+    tc_fence_after();
+  }
+  const bool next_qk = (j + 2) < n_sub;  // sub-tile j+2 lives in K tile (tile + 1), stage st_next
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {
+    const int n_w = w ? n_s1 : n_s0;
+    const uint32_t tS = w * 128 + sub * kSub;  // == P buffer
+    if (j < n_w) {
+      mbar_wait(&bars->p_ready[w][sub], tile & 1);
+      tc_fence_after();
+      // O_w (+)= P_w * V[j]: V tile is [keys][d] -> MN-major B, LBO 16 KiB (64-wide d blocks), SBO 1 KiB
+      const uint32_t b_lo = sb16 + ((kOffV + st * kTileBytes + sub * kSub * 128) >> 4) + desc_lo_lbo(kBoxBytes);
+      const uint32_t acc = (j > 0 || load_state) ? 1u : 0u;
+#pragma unroll
+      for (int kk = 0; kk < kSub / 16; ++kk)
+        umma_ts_lh(256 + w * 128, tS + kk * 8, b_lo + kk * (16 * 128 / 16), hi, idesc_pv, kk > 0 ? 1u : acc);
+      umma_commit(&bars->o_done[w]);
+      if (j == n_w - 1) umma_commit(&bars->o_final[w]);
+    }
+    if (w == 1 && sub == 1) umma_commit(&bars->v_empty[st]);
+    if (next_qk) {
+      if (w == 0 && sub == 0) {
+        mbar_wait(&bars->k_full[st_next], ((tile + 1) >> 1) & 1);
+        tc_fence_after();
+      }
+      if (j + 2 < n_w) {
+        // S_w = Q_w K^T for the 64 keys of sub-tile j+2 (8 KiB into each 64-wide box of the K tile)
+        const uint32_t a_lo = sb16 + ((kOffQ + w * kTileBytes) >> 4) + desc_lo_lbo(16);
+        const uint32_t k_lo = sb16 + ((kOffK + st_next * kTileBytes + sub * kSub * 128) >> 4) + desc_lo_lbo(16);
+#pragma unroll
+        for (int kk = 0; kk < kHeadDim / 16; ++kk) {
+          const uint32_t off = ((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4;
+          umma_ss_lh(tS, a_lo + off, hi, k_lo + off, hi, idesc_qk, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&bars->s_full[w][sub]);
+      }
+      if (w == 1 && sub == 1) umma_commit(&bars->k_empty[st_next]);
+    }
+  }
+}
 
 // number of 64-key sub-tiles a 128-row Q tile starting at r0 must visit
 __device__ __forceinline__ int fwd_trip_count(int r0, const FwdParams& p) {
@@ -83,12 +141,13 @@ template <bool kBF16, int kPoly>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                               // [2][32 KiB]
-  uint8_t* sK = sQ + 2 * kTileBytes;                // [kKStages][32 KiB]
-  uint8_t* sV = sK + kKStages * kTileBytes;         // [kVStages][32 KiB]
-  FwdBarriers* bars = reinterpret_cast<FwdBarriers*>(sV + kVStages * kTileBytes);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();      // SWIZZLE_128B atoms need a 1 KiB-aligned base
+  uint8_t* sQ = smem + kOffQ;                       // [2][32 KiB]
+  uint8_t* sK = smem + kOffK;                       // [kKStages][32 KiB]
+  uint8_t* sV = smem + kOffV;                       // [kVStages][32 KiB]
+  FwdBarriers* bars = reinterpret_cast<FwdBarriers*>(smem + kOffBars);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -133,7 +192,10 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
+  // all 512 columns are allocated, so the allocation starts at TMEM address 0; the MMA issue path
+  // relies on that to keep every TMEM address a compile-time constant
+  if (bars->tmem_base != 0) __trap();
+  constexpr uint32_t tmem_base = 0;
 
   if (warp == 9) {
     // ============================================================ TMA producer
@@ -160,81 +222,37 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp == 8) {
     // ============================================================ MMA issuer (whole warp, elected lane issues)
-    {
+    const uint32_t sb16 = smem_u32(smem) >> 4;
+    if (n_sub > 0) {
       constexpr uint32_t idesc_qk = make_idesc(kBF16, kBlockM, kSub, false, false);
-      constexpr uint32_t idesc_pv = make_idesc(kBF16, kBlockM, kHeadDim, false, true);
-      const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
-      const int n_s[2] = {n_s0, n_s1};
-
-      // S_w[j&1] = Q_w * K[j]^T for the 64 keys of sub-tile j: 8 k-steps of 16 over D=128
-      // (D split into two 64-wide SW128 boxes); the sub-tile's keys start 64 rows (8 KiB) into each box
-      auto issue_qk = [&](int w, int j) {
-        const int ks = (j >> 1) % kKStages;
-        const uint64_t a0 = make_smem_desc(smem_u32(sQ + w * kTileBytes), 16, 1024);
-        const uint64_t b0 = make_smem_desc(smem_u32(sK + ks * kTileBytes + (j & 1) * kSub * 128), 16, 1024);
-        const uint32_t tS = tmem_base + w * 128 + (j & 1) * kSub;
+      constexpr uint32_t hi = desc_hi(1024);
+      mbar_wait(&bars->q_full, 0);
+      mbar_wait(&bars->k_full[0], 0);
+      tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < kHeadDim / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
-          umma_ss(tS, desc_advance(a0, off), desc_advance(b0, off), idesc_qk, kk > 0 ? 1u : 0u);
-        }
-      };
-      // O_w (+)= P_w[j&1] * V[j]: 4 k-steps of 16 keys; V tile is [keys][d] -> MN-major B,
-      // LBO = 16 KiB between the two 64-wide d blocks, SBO = 1 KiB between 8-key groups
-      auto issue_pv = [&](int w, int j, bool acc) {
-        const int vs = (j >> 1) % kVStages;
-        const uint64_t b0 = make_smem_desc(smem_u32(sV + vs * kTileBytes + (j & 1) * kSub * 128), kBoxBytes, 1024);
-        const uint32_t tP = tmem_base + w * 128 + (j & 1) * kSub;
-#pragma unroll
-        for (int kk = 0; kk < kSub / 16; ++kk) {
-          umma_ts(tO[w], tP + kk * 8, desc_advance(b0, kk * 16 * 128), idesc_pv, (acc || kk > 0) ? 1u : 0u);
-        }
-      };
-
-      if (n_sub > 0) {
-        mbar_wait(&bars->q_full, 0);
-        mbar_wait(&bars->k_full[0], 0);
-        tc_fence_after();
-        for (int j = 0; j < 2; ++j)
-          for (int w = 0; w < 2; ++w)
-            if (j < n_s[w]) {
-              issue_qk(w, j);
-              umma_commit(&bars->s_full[w][j]);
-            }
-        umma_commit(&bars->k_empty[0]);
-      }
-      for (int j = 0; j < n_sub; ++j) {
-        const int tile = j >> 1, sub = j & 1;
-        const int vs = tile % kVStages;
-        if (sub == 0) {
-          mbar_wait(&bars->v_full[vs], (tile / kVStages) & 1);
-          tc_fence_after();
-        }
-        const bool next_qk = (j + 2) < n_sub;          // sub-tile j+2 lives in K tile (tile + 1)
-        const int ks_next = (tile + 1) % kKStages;
+      for (int j = 0; j < 2; ++j) {
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
-          if (j < n_s[w]) {
-            mbar_wait(&bars->p_ready[w][sub], tile & 1);
-            tc_fence_after();
-            issue_pv(w, j, (j > 0) || p.load_state);
-            umma_commit(&bars->o_done[w]);
-            if (j == n_s[w] - 1) umma_commit(&bars->o_final[w]);
-          }
-          if (w == 1 && sub == 1) umma_commit(&bars->v_empty[vs]);
-          if (next_qk) {
-            if (w == 0 && sub == 0) {
-              mbar_wait(&bars->k_full[ks_next], ((tile + 1) / kKStages) & 1);
-              tc_fence_after();
+          if (j < (w ? n_s1 : n_s0)) {
+            const uint32_t a_lo = sb16 + ((kOffQ + w * kTileBytes) >> 4) + desc_lo_lbo(16);
+            const uint32_t k_lo = sb16 + ((kOffK + j * kSub * 128) >> 4) + desc_lo_lbo(16);
+#pragma unroll
+            for (int kk = 0; kk < kHeadDim / 16; ++kk) {
+              const uint32_t off = ((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4;
+              umma_ss_lh(w * 128 + j * kSub, a_lo + off, hi, k_lo + off, hi, idesc_qk, kk > 0 ? 1u : 0u);
             }
-            if (j + 2 < n_s[w]) {
-              issue_qk(w, j + 2);
-              umma_commit(&bars->s_full[w][sub]);
-            }
-            if (w == 1 && sub == 1) umma_commit(&bars->k_empty[ks_next]);
+            umma_commit(&bars->s_full[w][j]);
           }
         }
       }
+      umma_commit(&bars->k_empty[0]);
+    }
+    const bool ls = p.load_state != 0;
+    for (int j0 = 0; j0 < n_sub; j0 += 4) {
+      fwd_mma_step<kBF16, 0>(j0, sb16, bars, n_s0, n_s1, n_sub, ls);
+      if (j0 + 1 < n_sub) fwd_mma_step<kBF16, 1>(j0 + 1, sb16, bars, n_s0, n_s1, n_sub, ls);
+      if (j0 + 2 < n_sub) fwd_mma_step<kBF16, 2>(j0 + 2, sb16, bars, n_s0, n_s1, n_sub, ls);
+      if (j0 + 3 < n_sub) fwd_mma_step<kBF16, 3>(j0 + 3, sb16, bars, n_s0, n_s1, n_sub, ls);
     }
   } else {
     // ============================================================ softmax warps

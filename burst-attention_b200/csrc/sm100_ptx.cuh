@@ -277,6 +277,41 @@ BA_DEVICE void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32
       : "memory");
 }
 
+// ---- lean issue path: descriptors as (lo, hi) 32-bit halves --------------------------------
+// The MMA issuer is ONE warp; every instruction it spends building 64-bit descriptors is time the
+// tensor pipe idles.  hi is a compile-time constant (SBO, version, swizzle); lo = start address >> 4
+// | LBO << 16 advances by plain 32-bit adds of compile-time constants.
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+}
+__host__ __device__ constexpr uint32_t desc_lo_lbo(uint32_t lbo_bytes) { return ((lbo_bytes >> 4) & 0x3FFF) << 16; }
+
+BA_DEVICE void umma_ss_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                          uint32_t idesc, uint32_t accumulate) {
+  if (elect_one())
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}\n"
+        :
+        : "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+BA_DEVICE void umma_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                          uint32_t accumulate) {
+  if (elect_one())
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n"
+        :
+        : "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // ------------------------------------------------------------------ packing
 template <bool kBF16>
 BA_DEVICE uint32_t pack2(float lo, float hi) {
