@@ -13,7 +13,8 @@ from typing import Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libburst_attn_b200.so")
+# BA_LIB_PATH: developer hook to A/B a differently built library (tools/); default is the in-tree build
+LIB_PATH = os.environ.get("BA_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "lib", "libburst_attn_b200.so")
 
 BA_DTYPE_FP16, BA_DTYPE_BF16 = 0, 1
 BA_MASK_NONE, BA_MASK_CAUSAL = 0, 1

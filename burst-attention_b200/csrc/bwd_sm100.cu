@@ -75,84 +75,6 @@ constexpr int kOffBar = kOffStat + 2 * 2 * kTile * 4;
 constexpr int kBwdSmemBytes = kOffBar + 256;  // no align slack: the dynamic smem base is checked to be 1 KiB aligned
 static_assert(kBwdSmemBytes <= 232448, "backward kernel exceeds 227 KiB of shared memory");
 
-// ---- MMA issue helpers: every smem descriptor / TMEM address is a compile-time constant apart from
-// sb16 = (dynamic smem base address) >> 4.  K-major operand k-step: +32 B inside a 128-B swizzle row,
-// +16 KiB to the second 64-wide box; MN-major operand k-step: +16 rows = 2 KiB.
-__host__ __device__ constexpr uint32_t kstep_k16(int kk) { return ((kk >> 2) * kBoxB + (kk & 3) * 32) >> 4; }
-__host__ __device__ constexpr uint32_t kstep_n16(int kk) { return (kk * 16 * 128) >> 4; }
-
-template <bool kBF16, int ST>
-__device__ __forceinline__ void bwd_issue_S(uint32_t sb16) {  // S^T = K Q_i^T (both K-major) -> TMEM [0,128)
-  constexpr uint32_t id = make_idesc(kBF16, 128, 128, false, false), hi = desc_hi(1024);
-  const uint32_t a = sb16 + (kOffK >> 4) + desc_lo_lbo(16);
-  const uint32_t b = sb16 + ((kOffQ + ST * kTileB) >> 4) + desc_lo_lbo(16);
-#pragma unroll
-  for (int kk = 0; kk < 8; ++kk) umma_ss_lh(0, a + kstep_k16(kk), hi, b + kstep_k16(kk), hi, id, kk > 0 ? 1u : 0u);
-}
-template <bool kBF16>
-__device__ __forceinline__ void bwd_issue_dP(uint32_t sb16) {  // dP^T = V dO_i^T (both K-major) -> TMEM [128,256)
-  constexpr uint32_t id = make_idesc(kBF16, 128, 128, false, false), hi = desc_hi(1024);
-  const uint32_t a = sb16 + (kOffV >> 4) + desc_lo_lbo(16);
-  const uint32_t b = sb16 + (kOffDO >> 4) + desc_lo_lbo(16);
-#pragma unroll
-  for (int kk = 0; kk < 8; ++kk) umma_ss_lh(128, a + kstep_k16(kk), hi, b + kstep_k16(kk), hi, id, kk > 0 ? 1u : 0u);
-}
-template <bool kBF16>
-__device__ __forceinline__ void bwd_issue_dV(uint32_t sb16, bool acc) {  // dV += P^T dO_i -> TMEM [384,512)
-  // P^T (16-bit) sits in TMEM over S^T: q 0..63 at cols [0,32), q 64..127 at cols [64,96); dO tile read MN-major
-  constexpr uint32_t id = make_idesc(kBF16, 128, 128, false, true), hi = desc_hi(1024);
-  const uint32_t b = sb16 + (kOffDO >> 4) + desc_lo_lbo(kBoxB);
-#pragma unroll
-  for (int kk = 0; kk < 8; ++kk)
-    umma_ts_lh(384, (kk >> 2) * 64 + (kk & 3) * 8, b + kstep_n16(kk), hi, id, (acc || kk > 0) ? 1u : 0u);
-}
-template <bool kBF16, int ST>
-__device__ __forceinline__ void bwd_issue_dK(uint32_t sb16, bool acc) {  // dK += dS^T Q_i -> TMEM [256,384)
-  constexpr uint32_t id = make_idesc(kBF16, 128, 128, false, true), hi = desc_hi(1024);
-  const uint32_t a = sb16 + (kOffDS >> 4) + desc_lo_lbo(16);                        // dS^T [key][q], K-major
-  const uint32_t b = sb16 + ((kOffQ + ST * kTileB) >> 4) + desc_lo_lbo(kBoxB);      // Q_i [q][d], MN-major
-#pragma unroll
-  for (int kk = 0; kk < 8; ++kk)
-    umma_ss_lh(256, a + kstep_k16(kk), hi, b + kstep_n16(kk), hi, id, (acc || kk > 0) ? 1u : 0u);
-}
-template <bool kBF16>
-__device__ __forceinline__ void bwd_issue_dQ(uint32_t sb16) {  // dQ_i = dS K -> TMEM [128,256) (over dP^T)
-  constexpr uint32_t id = make_idesc(kBF16, 128, 128, true, true), hi = desc_hi(1024);
-  const uint32_t a = sb16 + (kOffDS >> 4) + desc_lo_lbo(kBoxB);                     // the same dS^T tile, MN-major
-  const uint32_t b = sb16 + (kOffK >> 4) + desc_lo_lbo(kBoxB);                      // K [key][d], MN-major
-#pragma unroll
-  for (int kk = 0; kk < 8; ++kk) umma_ss_lh(128, a + kstep_n16(kk), hi, b + kstep_n16(kk), hi, id, kk > 0 ? 1u : 0u);
-}
-
-// One Q-block iteration of the MMA warp; ST = it & 1 is the Q stage (compile time).
-template <bool kBF16, int ST>
-__device__ __forceinline__ void bwd_mma_iter(int it, int n_it, uint32_t sb16, BwdBarriers* bars) {
-  const bool have_next = it + 1 < n_it;
-  mbar_wait(&bars->p_ready, it & 1);
-  tc_fence_after();
-  bwd_issue_dV<kBF16>(sb16, it > 0);
-  umma_commit(&bars->do_empty);
-  if (have_next) {
-    mbar_wait(&bars->q_full[ST ^ 1], ((it + 1) >> 1) & 1);
-    tc_fence_after();
-    bwd_issue_S<kBF16, ST ^ 1>(sb16);
-    umma_commit(&bars->s_full);
-  }
-  mbar_wait(&bars->ds_ready, it & 1);
-  tc_fence_after();
-  bwd_issue_dK<kBF16, ST>(sb16, it > 0);
-  umma_commit(&bars->q_empty[ST]);
-  bwd_issue_dQ<kBF16>(sb16);
-  umma_commit(&bars->dq_full);
-  if (have_next) {
-    mbar_wait(&bars->do_full, (it + 1) & 1);
-    mbar_wait(&bars->dq_free, it & 1);
-    tc_fence_after();
-    bwd_issue_dP<kBF16>(sb16);
-    umma_commit(&bars->dp_full);
-  }
-}
-
 template <bool kBF16>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -213,11 +135,8 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // all 512 columns are allocated -> the allocation starts at TMEM address 0 (keeps every TMEM
-  // address in the MMA issue path a compile-time constant)
-  if (bars->tmem_base != 0) __trap();
-  constexpr uint32_t tmem_base = 0;
-  constexpr uint32_t tS = 0, tDP = 128, tDK = 256, tDV = 384;
+  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDK = tmem_base + 256, tDV = tmem_base + 384;
 
   // register re-distribution (512 threads x 128 at launch): the MMA/load warpgroup donates to the
   // dQ-reduce warpgroup, which needs a whole 128-column TMEM row in registers to free TMEM early
@@ -266,21 +185,88 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp == 12) {
     // ============================================================ MMA issuer
+    // (A/B on one box: a fully unrolled constant-descriptor issue path like the forward's made this
+    //  kernel 7 % SLOWER -- 953 vs 1026 TFLOP/s -- the backward is bound by shared-memory operand
+    //  bandwidth, not by issue rate, so the compact rolled form below is kept.)
     reg_dec<64>();
     {
-      const uint32_t sb16 = smem_u32(smem) >> 4;
+      constexpr uint32_t id_kk = make_idesc(kBF16, 128, 128, false, false);  // A K-major, B K-major
+      constexpr uint32_t id_kn = make_idesc(kBF16, 128, 128, false, true);   // A K-major/TMEM, B MN-major
+      constexpr uint32_t id_nn = make_idesc(kBF16, 128, 128, true, true);    // A MN-major, B MN-major
+      const uint64_t dK_k = make_smem_desc(smem_u32(sK), 16, 1024);          // K tile as K-major A
+      const uint64_t dV_k = make_smem_desc(smem_u32(sV), 16, 1024);
+      const uint64_t dK_n = make_smem_desc(smem_u32(sK), kBoxB, 1024);       // K tile as MN-major B
+      const uint64_t dDO_k = make_smem_desc(smem_u32(sDO), 16, 1024);
+      const uint64_t dDO_n = make_smem_desc(smem_u32(sDO), kBoxB, 1024);
+      const uint64_t dDS_k = make_smem_desc(smem_u32(sDS), 16, 1024);        // dS^T [key][q] as K-major A
+      const uint64_t dDS_n = make_smem_desc(smem_u32(sDS), kBoxB, 1024);     // ... as MN-major A (M = q)
+
+      auto kstep_k = [](int kk) -> uint32_t { return (kk >> 2) * kBoxB + (kk & 3) * 32; };  // K-major k-step
+      auto kstep_n = [](int kk) -> uint32_t { return kk * 16 * 128; };                      // MN-major k-step
+
+      auto issue_S = [&](int st) {  // S^T = K Q^T
+        const uint64_t dQ_k = make_smem_desc(smem_u32(sQ + st * kTileB), 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tS, desc_advance(dK_k, kstep_k(kk)), desc_advance(dQ_k, kstep_k(kk)), id_kk, kk > 0);
+      };
+      auto issue_dP = [&]() {  // dP^T = V dO^T
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tDP, desc_advance(dV_k, kstep_k(kk)), desc_advance(dDO_k, kstep_k(kk)), id_kk, kk > 0);
+      };
+      auto issue_dV = [&](bool acc) {  // dV += P^T dO ; P^T cols: q 0..63 at [0,32), q 64..127 at [64,96)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ts(tDV, tS + (kk >> 2) * 64 + (kk & 3) * 8, desc_advance(dDO_n, kstep_n(kk)), id_kn, acc || kk > 0);
+      };
+      auto issue_dK = [&](int st, bool acc) {  // dK += dS^T Q
+        const uint64_t dQ_n = make_smem_desc(smem_u32(sQ + st * kTileB), kBoxB, 1024);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tDK, desc_advance(dDS_k, kstep_k(kk)), desc_advance(dQ_n, kstep_n(kk)), id_kn, acc || kk > 0);
+      };
+      auto issue_dQ = [&]() {  // dQ = dS K
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tDP, desc_advance(dDS_n, kstep_n(kk)), desc_advance(dK_n, kstep_n(kk)), id_nn, kk > 0);
+      };
+
       mbar_wait(&bars->kv_full, 0);
       mbar_wait(&bars->q_full[0], 0);
       tc_fence_after();
-      bwd_issue_S<kBF16, 0>(sb16);
+      issue_S(0);
       umma_commit(&bars->s_full);
       mbar_wait(&bars->do_full, 0);
       tc_fence_after();
-      bwd_issue_dP<kBF16>(sb16);
+      issue_dP();
       umma_commit(&bars->dp_full);
-      for (int it0 = 0; it0 < n_it; it0 += 2) {
-        bwd_mma_iter<kBF16, 0>(it0, n_it, sb16, bars);
-        if (it0 + 1 < n_it) bwd_mma_iter<kBF16, 1>(it0 + 1, n_it, sb16, bars);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        const bool have_next = it + 1 < n_it;
+        mbar_wait(&bars->p_ready, it & 1);
+        tc_fence_after();
+        issue_dV(it > 0);
+        umma_commit(&bars->do_empty);
+        if (have_next) {
+          mbar_wait(&bars->q_full[st ^ 1], ((it + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_S(st ^ 1);
+          umma_commit(&bars->s_full);
+        }
+        mbar_wait(&bars->ds_ready, it & 1);
+        tc_fence_after();
+        issue_dK(st, it > 0);
+        umma_commit(&bars->q_empty[st]);
+        issue_dQ();
+        umma_commit(&bars->dq_full);
+        if (have_next) {
+          mbar_wait(&bars->do_full, (it + 1) & 1);
+          mbar_wait(&bars->dq_free, it & 1);
+          tc_fence_after();
+          issue_dP();
+          umma_commit(&bars->dp_full);
+        }
       }
       umma_commit(&bars->dkv_full);
     }

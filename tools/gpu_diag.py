@@ -91,6 +91,11 @@ def perf_stage():
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
+    a = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+    bm = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+    ms = t(lambda: torch.matmul(a, bm), 10)
+    say(f"[perf calib cublas bf16 8192^3] ms={ms:.3f} tflops={2 * 8192 ** 3 / ms / 1e9:.1f}  lib={os.environ.get('BA_LIB_PATH', 'default')}")
+    del a, bm
     for causal in (False, True):
         f = lambda: ops.fwd_chunk(q, k, v, None, lse, out, 128 ** -0.5, causal, 0, True, True, 1)
         ms = t(f)
