@@ -162,6 +162,10 @@ def main():
     ap.add_argument("--causal", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--configs", default="", help="comma list of extra runs in the same process group, e.g. "
+                    "'262144,524288c,1048576' (c = causal zigzag); one JSON line each (multi-GPU sessions are "
+                    "expensive to start)")
+    ap.add_argument("--ring-check", action="store_true", help="run tools/ring_check.py's parity cases first")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -185,6 +189,26 @@ def main():
     native.check(native.lib().ba_device_check(), "ba_device_check")
     ops = chunk_ops.get_ops()
 
+    if args.ring_check and world > 1:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import ring_check
+        fails = ring_check.run_cases(rank, world, dev)
+        if rank == 0:
+            print(json.dumps({"ring_check": "PASS" if fails == 0 else f"{fails} FAILED", "world": world}), flush=True)
+
+    runs = [(args.seq, args.causal)]
+    if args.configs:
+        runs = [(int(c.rstrip("c")), c.endswith("c")) for c in args.configs.split(",") if c]
+    for seq_i, causal_i in runs:
+        args.seq, args.causal = seq_i, causal_i
+        _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func)
+        torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
     S = args.seq
     S_loc = S // world
     layout = "zigzag" if args.causal else "contiguous"
@@ -223,6 +247,7 @@ def main():
     # ---- warm-up (also builds the NCCL ring)
     for _ in range(W):
         step(q, k, v, do)
+    ops.launches = ops.launches  # (counter keeps running; deltas are taken around the timed region)
     torch.cuda.synchronize()
 
     # ---- timed: fwd+bwd, inputs resident in HBM; per-kernel events on the launching stream
@@ -304,10 +329,7 @@ def main():
             "gpu_launches": int(tot_launch.item()), "clocks": clocks, "e2e": e2e, "roofline": roof,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

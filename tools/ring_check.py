@@ -20,6 +20,13 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    fails = run_cases(rank, world, dev)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(1 if fails else 0)
+
+
+def run_cases(rank, world, dev):
     n_heads = int(os.environ.get("RING_CHECK_HEADS", "8"))
     fails = 0
     for dtype, tol in ((torch.float16, dict(rtol=1e-3, atol=1e-2)), (torch.bfloat16, dict(rtol=1.6e-2, atol=2e-2))):
@@ -52,9 +59,7 @@ def main():
             if rank == 0:
                 print(f"ring_check W={world} {name:8s} {str(dtype):15s} {'PASS' if flag.item() == 0 else 'FAIL'}", flush=True)
             fails += int(flag.item())
-    dist.barrier()
-    dist.destroy_process_group()
-    sys.exit(1 if fails else 0)
+    return fails
 
 
 if __name__ == "__main__":
