@@ -31,7 +31,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 H, D, B = 32, 128, 1
-METRIC = "attention fwd+bwd TFLOPS/s at seq=262144 (bs=1, H=32, d=128, bf16), aggregate over GPUs"
+METRIC = "attention fwd+bwd TFLOPS/s (bs=1, H=32, d=128, bf16; seq in config, default 262144), aggregate over GPUs"
 
 
 def flops(S, mode):
