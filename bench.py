@@ -291,6 +291,16 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
                                   "avg_launch_ms": tot_f / n_f,
                                   "frac": fl_f / (tot_f / n_f * 1e-3) / 1e12 / pk["sustained"]}
 
+    # ---- how much of the step is NOT inside one of our kernels on the compute stream: torch memsets /
+    # allocations, launch gaps and any ring-communication time the kernels did not hide (upper bound
+    # on exposed comm; target < 5 %)
+    overlap = None
+    if kms:
+        k_ms = sum(t for _, t in kms.values()) / K
+        overlap = {"kernel_ms_per_step": k_ms, "non_kernel_ms_per_step": ms_step - k_ms,
+                   "non_kernel_frac": (ms_step - k_ms) / ms_step,
+                   "per_kernel_ms_per_step": {n: t / K for n, (c, t) in kms.items()}}
+
     # ---- e2e: same step through the public API from pinned host buffers
     e2e = None
     if not args.no_e2e:
@@ -326,7 +336,7 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
                        "global_batch": B, "seq_len": S, "parallelism": f"sp{world}",
                        "l2": "inputs (>= 256 MiB per tensor per rank) exceed the 126 MB L2; no flush needed"},
             "value_per_gpu": value / world, "fwd_tflops": fwd_tflops, "fwd_ms": ms_fwd,
-            "gpu_launches": int(tot_launch.item()), "clocks": clocks, "e2e": e2e, "roofline": roof,
+            "gpu_launches": int(tot_launch.item()), "clocks": clocks, "e2e": e2e, "roofline": roof, "overlap": overlap,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -69,9 +69,11 @@ class NativeOps:
     # ---- delta = rowsum(O * dO)
     def delta(self, o, d_o, out, seq_dim):
         B, S, H, D = _dims(o, seq_dim)
+        e0 = self._t0(o.device)
         rc = self.lib.ba_bwd_delta(_n.t4(o, seq_dim), _n.t4(d_o, seq_dim), _n.rs(out), B, S, H, D,
                                    _n.dtype_code(o.dtype), _n.stream_ptr(o.device))
         _n.check(rc, "ba_bwd_delta")
+        self._t1("delta_kernel", e0, o.device)
         self.launches += 1
 
     # ---- backward round: accumulate into fp32 dq_acc / dk_acc / dv_acc
@@ -92,17 +94,21 @@ class NativeOps:
     # ---- dst (16-bit) = src (fp32)
     def cast(self, src, dst, seq_dim):
         B, S, H, D = _dims(src, seq_dim)
+        e0 = self._t0(src.device)
         rc = self.lib.ba_cast_from_f32(_n.t4(src, seq_dim), _n.t4(dst, seq_dim), B, S, H, D,
                                        _n.dtype_code(dst.dtype), _n.stream_ptr(src.device))
         _n.check(rc, "ba_cast_from_f32")
+        self._t1("cast_kernel", e0, src.device)
         self.launches += 1
 
     # ---- dst (fp32) += src (fp32)
     def accumulate(self, src, dst, seq_dim):
         B, S, H, D = _dims(src, seq_dim)
+        e0 = self._t0(src.device)
         rc = self.lib.ba_accumulate_f32(_n.t4(src, seq_dim), _n.t4(dst, seq_dim), B, S, H, D,
                                         _n.stream_ptr(src.device))
         _n.check(rc, "ba_accumulate_f32")
+        self._t1("accumulate_kernel", e0, src.device)
         self.launches += 1
 
 

@@ -53,7 +53,17 @@ struct BwdParams {
   int B, Sq, Sk, H;
   float scale, scale_log2;
   int causal, causal_off;
+  int* sem;  // deterministic mode: [B][H][nQ] turn counters ordering the dQ reductions by key block; else null
 };
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 struct __align__(8) BwdBarriers {
   uint64_t kv_full;
@@ -291,6 +301,13 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->dq_free);
+      // deterministic mode: the fp32 adds into dq_acc[q block] happen in key-block order.  Key blocks that
+      // see a given Q block are 0..x_max, and lower blockIdx.x are dispatched first, so waiting for our
+      // turn cannot deadlock.
+      int* turn = p.sem ? p.sem + ((int64_t)b * p.H + h) * nQ + (i_begin + it) : nullptr;
+      if (turn && issuer) {
+        while (ld_acquire_gpu(turn) != (int)blockIdx.x) __nanosleep(64);
+      }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint8_t* stage = sDQ + (c & 1) * kDqStageB;
@@ -312,6 +329,11 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tma_reduce_add_4d(&tmDQ, stage, c * 32, h, q0, b);
           tma_store_commit();
         }
+      }
+      if (turn && issuer) {
+        tma_store_wait<0>();  // our four reductions have been performed ...
+        __threadfence();
+        st_release_gpu(turn, (int)blockIdx.x + 1);  // ... next key block's turn
       }
     }
     if (issuer) tma_store_wait<0>();
@@ -449,6 +471,24 @@ static int launch_bwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUte
   return BA_OK;
 }
 
+// one-time (grown on demand) workspace for the deterministic-mode turn counters
+static int* bwd_sem_workspace(size_t n_ints, cudaStream_t stream) {
+  static int* ws = nullptr;
+  static size_t cap = 0;
+  static int ws_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  if (ws == nullptr || cap < n_ints || ws_dev != dev) {
+    if (ws) cudaFree(ws);
+    ws = nullptr;
+    if (cudaMalloc(&ws, n_ints * sizeof(int)) != cudaSuccess) return nullptr;
+    cap = n_ints;
+    ws_dev = dev;
+  }
+  if (cudaMemsetAsync(ws, 0, n_ints * sizeof(int), stream) != cudaSuccess) return nullptr;
+  return ws;
+}
+
 static bool f32_view_ok(const ba_tensor4& t) {
   return t.ptr && (reinterpret_cast<uintptr_t>(t.ptr) & 15) == 0 && t.stride_b % 4 == 0 && t.stride_s % 4 == 0 &&
          t.stride_h % 4 == 0;
@@ -470,7 +510,6 @@ extern "C" int ba_bwd_chunk(ba_tensor4 d_o, ba_tensor4 q, ba_tensor4 k, ba_tenso
   BA_REQUIRE(f32_view_ok(dq_acc) && f32_view_ok(dk_acc) && f32_view_ok(dv_acc),
              "ba_bwd_chunk: fp32 accumulators must be non-null, 16-byte aligned, strides multiple of 4");
   BA_REQUIRE(H <= 65535 && B <= 65535, "ba_bwd_chunk: H and B must be <= 65535");
-  (void)flags;  // BA_BWD_DETERMINISTIC: dQ is reduced with fp32 adds in L2 (order not fixed) -- see DESIGN.md
 
   CUtensorMap tmQ, tmK, tmV, tmDO, tmDQ;
   const CUtensorMapDataType dt = lowp_dtype(dtype);
@@ -495,6 +534,15 @@ extern "C" int ba_bwd_chunk(ba_tensor4 d_o, ba_tensor4 q, ba_tensor4 k, ba_tenso
   p.causal = mask_mode == BA_MASK_CAUSAL;
   p.causal_off = causal_offset;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p.sem = nullptr;
+  if (flags & BA_BWD_DETERMINISTIC) {
+    const size_t n = (size_t)B * H * ((Sq + kTile - 1) / kTile);
+    p.sem = bwd_sem_workspace(n, st);
+    if (!p.sem) {
+      set_error("ba_bwd_chunk: could not allocate the deterministic-mode workspace (%zu ints)", n);
+      return BA_ERR_CUDA;
+    }
+  }
   return dtype == BA_DTYPE_BF16 ? launch_bwd<true>(tmQ, tmK, tmV, tmDO, tmDQ, p, st)
                                 : launch_bwd<false>(tmQ, tmK, tmV, tmDO, tmDQ, p, st);
 }

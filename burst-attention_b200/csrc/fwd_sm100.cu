@@ -154,7 +154,8 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
-  const int row0 = blockIdx.x * (2 * kBlockM);
+  // causal: the last Q tiles see the most keys -- schedule them first (longest-processing-time order)
+  const int row0 = (p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * (2 * kBlockM);
   const int n_s0 = fwd_trip_count(row0, p);            // sub-tiles for Q tile 0 / 1
   const int n_s1 = fwd_trip_count(row0 + kBlockM, p);
   const int n_sub = max(n_s0, n_s1);
@@ -535,7 +536,7 @@ fwd3_chunk_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
-  const int row0 = blockIdx.x * (2 * kBlockM);
+  const int row0 = (p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * (2 * kBlockM);
   const int n_s0 = fwd_trip_count(row0, p);
   const int n_s1 = fwd_trip_count(row0 + kBlockM, p);
   const int n_sub = max(n_s0, n_s1);

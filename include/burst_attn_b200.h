@@ -45,7 +45,7 @@ extern "C" {
 #define BA_FWD_LAST 2  /* write the normalised output in the input dtype to o_out             */
 
 /* flags for ba_bwd_chunk */
-#define BA_BWD_DETERMINISTIC 1 /* reserved: ordered dQ reduction                              */
+#define BA_BWD_DETERMINISTIC 1 /* dQ reduced in key-block order (bitwise reproducible, slower)   */
 
 /* A [b,s,h,d] view: d is contiguous, the other strides are in elements. */
 typedef struct {

@@ -95,3 +95,52 @@ def test_cast_and_accumulate():
     half = torch.zeros(2, 50, 3, 128, device="cuda", dtype=torch.float16)
     ops.cast(src.narrow(1, 50, 50), half, 1)
     assert torch.equal(half, src[:, 50:].to(torch.float16))
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_bwd_deterministic_is_bitwise_reproducible(causal):
+    """deterministic=True (reference: forwarded to flash-attn, burst_attn_interface.py:318-320):
+    dQ is reduced in key-block order -> identical bits run to run, same values as the oracle."""
+    dtype = torch.bfloat16
+    B, S, H = 1, 2048, 4
+    q, do, k, v = (_mk(B, S, H, dtype, s) for s in (21, 22, 23, 24))
+    ops = NativeOps()
+    scale = 128 ** -0.5
+    o, lse = orc.dense_attention(q.cpu(), k.cpu(), v.cpu(), scale, causal)
+    delta = orc.compute_delta(o, do.cpu()).float().cuda()
+    lse = lse.float().cuda()
+    outs = []
+    for _ in range(3):
+        acc = [torch.zeros(t.shape, device="cuda", dtype=torch.float32) for t in (q, k, v)]
+        ops.bwd_chunk(do, q, k, v, delta, lse, acc[0], acc[1], acc[2], scale, causal, 0, 1, deterministic=True)
+        torch.cuda.synchronize()
+        outs.append(acc)
+    for a in outs[1:]:
+        for x, y in zip(a, outs[0]):
+            assert torch.equal(x, y)
+    _, _, rdq, rdk, rdv = orc.dense_attention_bwd(q.cpu(), k.cpu(), v.cpu(), do.cpu(), scale, causal)
+    for g, r in zip(outs[0], (rdq, rdk, rdv)):
+        torch.testing.assert_close(g.double().cpu(), r, **TOL[dtype])
+
+
+def test_bwd_large_property_dv_linear_in_do():
+    """Size-independent property at a size the oracle cannot finish: dV is linear in dO (delta, lse fixed
+    per call), and dK/dQ/dV of one head match torch SDPA's autograd on the GPU."""
+    dtype = torch.bfloat16
+    B, S, H = 1, 4096, 2
+    q, k, v, do = (_mk(B, S, H, dtype, s) for s in (31, 32, 33, 34))
+    qq, kk, vv = (t.float().permute(0, 2, 1, 3).clone().requires_grad_() for t in (q, k, v))
+    o_ref = torch.nn.functional.scaled_dot_product_attention(qq, kk, vv)
+    g = torch.autograd.grad(o_ref, (qq, kk, vv), do.float().permute(0, 2, 1, 3))
+    ops = NativeOps()
+    scale = 128 ** -0.5
+    out = torch.empty_like(q)
+    lse = torch.empty(B, H, S, device="cuda")
+    ops.fwd_chunk(q, k, v, None, lse, out, scale, False, 0, True, True, 1)
+    delta = torch.empty(B, H, S, device="cuda")
+    ops.delta(out, do, delta, 1)
+    acc = [torch.zeros(t.shape, device="cuda") for t in (q, k, v)]
+    ops.bwd_chunk(do, q, k, v, delta, lse, acc[0], acc[1], acc[2], scale, False, 0, 1)
+    torch.cuda.synchronize()
+    for got, ref in zip(acc, g):
+        torch.testing.assert_close(got, ref.permute(0, 2, 1, 3), rtol=2e-2, atol=2e-2)
