@@ -18,6 +18,7 @@ before the round's kernel and awaited after it.
 from __future__ import annotations
 
 import math
+import os
 from typing import List
 
 import torch
@@ -47,6 +48,69 @@ def _half(t, dim, idx):
     return t.narrow(dim, 0, n) if idx == 0 else t.narrow(dim, n, t.shape[dim] - n)
 
 
+def _l2_block() -> int:
+    """Rows/keys per sub-launch.  One (batch, head) slice of 32768 keys is 16 MiB of K+V (or 32 MiB of
+    Q, dO and fp32 dQ in the backward), so the streamed operands of a launch stay resident in B200's
+    126 MB L2 while all CTAs of a head sweep them -- measured +20 % at S=262144 on one GPU compared
+    with a single launch over the whole sequence.  The multi-GPU rounds at S_local <= 49152 are
+    unaffected.  BA_L2_BLOCK overrides (tests use tiny blocks)."""
+    return int(os.environ.get("BA_L2_BLOCK", "32768"))
+
+
+def _fwd_round(ops, q, k, v, o_acc, lse, out, scale, causal, off, first, last, seq_dim):
+    """One forward ring round, split over K/V blocks that fit L2 (each block is one kernel launch with
+    the carried state; the state pass costs 2 x 512 B per row and head, the block > 8 MB of math)."""
+    blk = _l2_block()
+    Sq, Sk = q.shape[seq_dim], k.shape[seq_dim]
+    if Sk <= blk + blk // 2:
+        ops.fwd_chunk(q, k, v, o_acc, lse, out, scale, causal, off, first, last, seq_dim)
+        return
+    n = (Sk + blk - 1) // blk
+    for c in range(n):
+        c0 = c * blk
+        kc, vc = k.narrow(seq_dim, c0, min(blk, Sk - c0)), v.narrow(seq_dim, c0, min(blk, Sk - c0))
+        if not causal:
+            ops.fwd_chunk(q, kc, vc, o_acc, lse, out, scale, False, 0, first and c == 0, last and c == n - 1, seq_dim)
+            continue
+        # causal: rows before r_start see none of this block's keys (key c0+b visible to row a iff
+        # c0 + b <= a + off); keep r_start on a tile-pair boundary
+        r_start = max(0, (c0 - off) // 256 * 256)
+        if r_start >= Sq:
+            break
+        ops.fwd_chunk(q.narrow(seq_dim, r_start, Sq - r_start), kc, vc,
+                      o_acc.narrow(seq_dim, r_start, Sq - r_start), lse.narrow(2, r_start, Sq - r_start), None,
+                      scale, True, r_start + off - c0, first and c == 0, False, seq_dim)
+    if causal and last:
+        ops.cast(o_acc, out, seq_dim)
+
+
+def _fwd_round_needs_state(k, seq_dim) -> bool:
+    blk = _l2_block()
+    return k.shape[seq_dim] > blk + blk // 2
+
+
+def _bwd_round(ops, g, q, k, v, delta, lse, dq_part, dk_acc, dv_acc, scale, causal, off, seq_dim, deterministic):
+    """One backward ring round, split over blocks of Q-bundle rows that fit L2."""
+    blk = _l2_block()
+    Sq, Sk = q.shape[seq_dim], k.shape[seq_dim]
+    if Sq <= blk + blk // 2:
+        ops.bwd_chunk(g, q, k, v, delta, lse, dq_part, dk_acc, dv_acc, scale, causal, off, seq_dim, deterministic)
+        return
+    for r0 in range(0, Sq, blk):
+        n = min(blk, Sq - r0)
+        kk, vv, dk, dv, o2 = k, v, dk_acc, dv_acc, off
+        if causal:
+            kmax = min(Sk, r0 + n + off)  # keys visible to the last row of this block
+            if kmax <= 0:
+                continue
+            kk, vv = k.narrow(seq_dim, 0, kmax), v.narrow(seq_dim, 0, kmax)
+            dk, dv = dk_acc.narrow(seq_dim, 0, kmax), dv_acc.narrow(seq_dim, 0, kmax)
+            o2 = off + r0
+        ops.bwd_chunk(g.narrow(seq_dim, r0, n), q.narrow(seq_dim, r0, n), kk, vv, delta.narrow(2, r0, n),
+                      lse.narrow(2, r0, n), dq_part.narrow(seq_dim, r0, n), dk, dv, scale, causal, o2, seq_dim,
+                      deterministic)
+
+
 def _check_inputs(q, k, v, seq_dim):
     assert q.dim() == 4 and k.shape == v.shape and q.shape[0] == k.shape[0] and q.shape[3] == k.shape[3], \
         "q, k, v must be 4-D with matching batch and head_dim"
@@ -67,7 +131,8 @@ def _ring_forward(q, k, v, scale, seq_dim, mode, process_group):
         assert S % 2 == 0, "zigzag causal sharding needs an even local sequence length"
     out = torch.empty_like(q)
     lse = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
-    o_acc = torch.empty(q.shape, dtype=torch.float32, device=q.device) if W > 1 else None
+    need_state = W > 1 or _fwd_round_needs_state(k, seq_dim)
+    o_acc = torch.empty(q.shape, dtype=torch.float32, device=q.device) if need_state else None
     if W > 1:
         k, v = k.contiguous(), v.contiguous()
     recv = [[torch.empty_like(k), torch.empty_like(v)] for _ in range(min(2, W - 1))]
@@ -79,21 +144,21 @@ def _ring_forward(q, k, v, scale, seq_dim, mode, process_group):
             ring.post([cur_k, cur_v], nxt)
         first, last = r == 1, r == W
         if mode == "none":
-            ops.fwd_chunk(q, cur_k, cur_v, o_acc, lse, out, scale, False, 0, first, last, seq_dim)
+            _fwd_round(ops, q, cur_k, cur_v, o_acc, lse, out, scale, False, 0, first, last, seq_dim)
         elif mode == "zigzag":
             if r == 1:  # own shard: plain causal (:221-224)
-                ops.fwd_chunk(q, cur_k, cur_v, o_acc, lse, out, scale, True, 0, first, last, seq_dim)
+                _fwd_round(ops, q, cur_k, cur_v, o_acc, lse, out, scale, True, 0, first, last, seq_dim)
             elif j < i:  # split_kv: all Q x first half of K/V (:225-231)
-                ops.fwd_chunk(q, _half(cur_k, seq_dim, 0), _half(cur_v, seq_dim, 0), o_acc, lse, out, scale,
-                              False, 0, False, last, seq_dim)
+                _fwd_round(ops, q, _half(cur_k, seq_dim, 0), _half(cur_v, seq_dim, 0), o_acc, lse, out, scale,
+                           False, 0, False, last, seq_dim)
             else:  # second half of Q x all K/V, merged into the second half of the state (:232-235)
-                ops.fwd_chunk(_half(q, seq_dim, 1), cur_k, cur_v, _half(o_acc, seq_dim, 1), _half(lse, 2, 1),
-                              _half(out, seq_dim, 1), scale, False, 0, False, last, seq_dim)
+                _fwd_round(ops, _half(q, seq_dim, 1), cur_k, cur_v, _half(o_acc, seq_dim, 1), _half(lse, 2, 1),
+                           _half(out, seq_dim, 1), scale, False, 0, False, last, seq_dim)
                 if last:  # rows the last round did not visit: hand their finished state over
                     ops.cast(_half(o_acc, seq_dim, 0), _half(out, seq_dim, 0), seq_dim)
         elif mode == "striped":
             # source rank ahead of us -> strictly-lower-triangular (causal_shift, :454,:463-475)
-            ops.fwd_chunk(q, cur_k, cur_v, o_acc, lse, out, scale, True, -1 if j > i else 0, first, last, seq_dim)
+            _fwd_round(ops, q, cur_k, cur_v, o_acc, lse, out, scale, True, -1 if j > i else 0, first, last, seq_dim)
         else:
             raise ValueError(mode)
         if r != W:
@@ -126,21 +191,21 @@ def _ring_backward(d_o, q, k, v, out, lse, scale, seq_dim, mode, process_group, 
     def round_kernel(r, j, bundle, dq_part):
         dlt, g, qq, ls = bundle
         if mode == "none":
-            ops.bwd_chunk(g, qq, k, v, dlt, ls, dq_part, dk_acc, dv_acc, scale, False, 0, seq_dim, deterministic)
+            _bwd_round(ops, g, qq, k, v, dlt, ls, dq_part, dk_acc, dv_acc, scale, False, 0, seq_dim, deterministic)
         elif mode == "zigzag":
             if r == 1:
-                ops.bwd_chunk(g, qq, k, v, dlt, ls, dq_part, dk_acc, dv_acc, scale, True, 0, seq_dim, deterministic)
+                _bwd_round(ops, g, qq, k, v, dlt, ls, dq_part, dk_acc, dv_acc, scale, True, 0, seq_dim, deterministic)
             elif j < i:  # split_q: second half of the bundle x all K/V (:322-345,:383-386)
-                ops.bwd_chunk(_half(g, seq_dim, 1), _half(qq, seq_dim, 1), k, v, _half(dlt, 2, 1), _half(ls, 2, 1),
-                              _half(dq_part, seq_dim, 1), dk_acc, dv_acc, scale, False, 0, seq_dim, deterministic)
+                _bwd_round(ops, _half(g, seq_dim, 1), _half(qq, seq_dim, 1), k, v, _half(dlt, 2, 1), _half(ls, 2, 1),
+                           _half(dq_part, seq_dim, 1), dk_acc, dv_acc, scale, False, 0, seq_dim, deterministic)
             else:  # whole bundle x first half of K/V (:347-367,:387-390)
-                ops.bwd_chunk(g, qq, _half(k, seq_dim, 0), _half(v, seq_dim, 0), dlt, ls, dq_part,
-                              _half(dk_acc, seq_dim, 0), _half(dv_acc, seq_dim, 0), scale, False, 0, seq_dim,
-                              deterministic)
+                _bwd_round(ops, g, qq, _half(k, seq_dim, 0), _half(v, seq_dim, 0), dlt, ls, dq_part,
+                           _half(dk_acc, seq_dim, 0), _half(dv_acc, seq_dim, 0), scale, False, 0, seq_dim,
+                           deterministic)
         elif mode == "striped":
             # K/V home on i, bundle from j: strict iff j < i (causal_shift, :529)
-            ops.bwd_chunk(g, qq, k, v, dlt, ls, dq_part, dk_acc, dv_acc, scale, True, -1 if j < i else 0, seq_dim,
-                          deterministic)
+            _bwd_round(ops, g, qq, k, v, dlt, ls, dq_part, dk_acc, dv_acc, scale, True, -1 if j < i else 0, seq_dim,
+                       deterministic)
         else:
             raise ValueError(mode)
 

@@ -85,6 +85,10 @@ def _mask(sq: int, sk: int, mask_mode: str, device=None) -> Optional[torch.Tenso
         return None
     a = torch.arange(sq, device=device).unsqueeze(1)
     b = torch.arange(sk, device=device).unsqueeze(0)
+    if isinstance(mask_mode, tuple) and mask_mode[0] == "causal_offset":
+        # the kernels' general form: key b visible to row a iff b <= a + offset (views of a larger
+        # causal problem: offset = row_start + off - key_start)
+        return b <= a + int(mask_mode[1])
     if mask_mode == "causal":
         return b <= a + (sk - sq)
     if mask_mode == "causal_strict":

@@ -15,8 +15,7 @@ def _bshd(t, seq_dim):
 def _mode(causal, off, sq, sk):
     if not causal:
         return "none"
-    assert sq == sk, "oracle ops: causal rounds are square"
-    return {0: "causal", -1: "causal_strict"}[off]
+    return ("causal_offset", off)
 
 
 class OracleOps:

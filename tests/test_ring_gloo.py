@@ -73,7 +73,8 @@ def _worker(rank, world, port, case, seq_dim, errq):
         # one chunk launch per round, no copies: W forward rounds (+1 cast in the zigzag tail case)
         nf = sum(1 for c in ops.calls if c[0] == "fwd")
         nb = sum(1 for c in ops.calls if c[0] == "bwd")
-        assert nf == world and nb == world, (nf, nb)
+        if not os.environ.get("BA_TEST_NO_LAUNCH_COUNT"):
+            assert nf == world and nb == world, (nf, nb)
         dist.barrier()
         dist.destroy_process_group()
     except Exception as e:  # noqa: BLE001
@@ -136,3 +137,53 @@ def test_single_process_world1_cpu():
                 torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5)
     finally:
         chunk_ops._set_ops_for_testing(None)
+
+
+@pytest.mark.parametrize("blk", [16, 24])
+def test_l2_blocking_of_rounds_matches_dense(monkeypatch, blk):
+    """The driver splits a round into L2-sized sub-launches (carried state forward, row blocks backward,
+    causal offsets for views); with a tiny block size every code path runs on CPU."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from burst_attn import burst_attn_func, burst_attn_func_striped, chunk_ops
+    from oracle import attention_oracle as orc
+    from oracle_ops import OracleOps
+    monkeypatch.setenv("BA_L2_BLOCK", str(blk))
+    ops = OracleOps()
+    chunk_ops._set_ops_for_testing(ops)
+    try:
+        torch.manual_seed(3)
+        S = 100  # ragged against the block size and far above 1.5 blocks
+        q, k, v, do = (torch.randn(2, S, 2, 16, dtype=torch.float64) for _ in range(4))
+        for func, causal in ((burst_attn_func, False), (burst_attn_func, True), (burst_attn_func_striped, True)):
+            ops.calls.clear()
+            qq, kk, vv = (t.clone().requires_grad_() for t in (q, k, v))
+            o = func(qq, kk, vv, None, "cuda", causal)
+            g = torch.autograd.grad(o, (qq, kk, vv), do)
+            o_ref, _, dq, dk, dv = orc.dense_attention_bwd(q, k, v, do, None, causal)
+            torch.testing.assert_close(o.detach(), o_ref, rtol=1e-5, atol=1e-5)
+            for a, b in zip(g, (dq, dk, dv)):
+                torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5)
+            assert sum(1 for c in ops.calls if c[0] == "fwd") > 1 and sum(1 for c in ops.calls if c[0] == "bwd") > 1
+    finally:
+        chunk_ops._set_ops_for_testing(None)
+
+
+@pytest.mark.parametrize("case", ["none", "zigzag", "striped"])
+def test_ring_driver_with_l2_blocking_world2(case, monkeypatch):
+    """Ring rounds + L2 blocking together (blocks of 8 rows/keys, S_local = 16): half views of the
+    zigzag rounds and the causal offsets compose."""
+    monkeypatch.setenv("BA_L2_BLOCK", "8")
+    monkeypatch.setenv("BA_TEST_NO_LAUNCH_COUNT", "1")
+    ctx = mp.get_context("spawn")
+    errq = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, 1, errq)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    errs = []
+    while not errq.empty():
+        errs.append(errq.get())
+    assert not errs, "\n".join(errs)
+    assert all(p.exitcode == 0 for p in procs)
