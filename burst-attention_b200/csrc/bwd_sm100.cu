@@ -230,11 +230,16 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int kk = 0; kk < 8; ++kk)
           umma_ts(tDV, tS + (kk >> 2) * 64 + (kk & 3) * 8, desc_advance(dDO_n, kstep_n(kk)), id_kn, acc || kk > 0);
       };
-      auto issue_dK = [&](int st, bool acc) {  // dK += dS^T Q
+      // dK += dS^T Q with dS^T (16-bit) read from TMEM, where the compute warps left it over the
+      // dP^T columns they had just consumed (q 0..63 at [128,160), q 64..127 at [192,224)).  TS form:
+      // only Q_i (4 KiB per MMA) comes from shared memory -- tcgen05 fetches smem operands at only
+      // ~64 B/clk, so an SS MMA with 8 KiB of operands runs at about half rate.  The dQ MMA issued
+      // right behind overwrites these columns; the tensor pipe executes in order, so that is safe.
+      auto issue_dK = [&](int st, bool acc) {
         const uint64_t dQ_n = make_smem_desc(smem_u32(sQ + st * kTileB), kBoxB, 1024);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_ss(tDK, desc_advance(dDS_k, kstep_k(kk)), desc_advance(dQ_n, kstep_n(kk)), id_kn, acc || kk > 0);
+          umma_ts(tDK, tDP + (kk >> 2) * 64 + (kk & 3) * 8, desc_advance(dQ_n, kstep_n(kk)), id_kn, acc || kk > 0);
       };
       auto issue_dQ = [&]() {  // dQ = dS K
 #pragma unroll
@@ -417,7 +422,11 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           uint4 o = make_uint4(dp[j * 4 + 0], dp[j * 4 + 1], dp[j * 4 + 2], dp[j * 4 + 3]);
           *reinterpret_cast<uint4*>(ds_row + (((half * 4 + j) ^ (r & 7)) << 4)) = o;
         }
+        // ... and the same 16 packed registers into TMEM (A operand of the dK MMA), over dP^T columns
+        // this thread has already read
+        tmem_st_x16(tDP + lane_base + hf * 64 + half * 16, dp);
       }
+      tmem_wait_st();
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
