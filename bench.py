@@ -280,8 +280,12 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
         # 10*Sq*Sk*H*D per round) / launches per step; non-causal: exactly 10*S_loc^2*H*D per ring round
         fl_launch = flops(S, "bwd") / causal_div / world / (n_l / K)
         ach = fl_launch / (tot_ms / n_l * 1e-3) / 1e12
+        # DRAM traffic per launch from the committed ncu --set full capture (profiles/ncu_bwd_r01_final.txt:
+        # dram__bytes_read 2.863 GB + write 1.771 GB) -- valid for the launch shape it was taken on
+        # (Sq = Sk = 32768 per launch, H=32, non-causal: every multi-GPU ring round at S_local=32768)
+        traffic = 4.634e9 if (S_loc == 32768 and not args.causal and n_l == K * world) else None
         roof = {"kernel": "bwd_chunk_kernel", "bound": "tensor", "achieved": ach, "peak": pk["sustained"],
-                "unit": "TFLOP/s", "frac": ach / pk["sustained"], "traffic": None,
+                "unit": "TFLOP/s", "frac": ach / pk["sustained"], "traffic": traffic,
                 "peak_source": pk["source"] + " bf16_tflops_sustained (of measured)",
                 "launches": n_l, "avg_launch_ms": tot_ms / n_l}
         if "fwd_chunk_kernel" in kms:
