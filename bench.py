@@ -327,7 +327,7 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
         dist.all_reduce(tot_launch)
 
     if rank == 0:
-        cpu = None if args.no_cpu else cpu_baseline()
+        cpu = None if (args.no_cpu or world > 1) else cpu_baseline()  # reported on rank 0 at N=1 only
         # the reference's README publishes 191 TFLOPS/s/GPU fwd+bwd at S=262144 on 8 GPUs (8xA100)
         vs = value / (191.0 * 8) if (world == 8 and S == 262144 and not args.causal) else None
         line = {
