@@ -34,8 +34,8 @@ H, D, B = 32, 128, 1
 METRIC = "attention fwd+bwd TFLOPS/s (bs=1, H=32, d=128, bf16; seq in config, default 262144), aggregate over GPUs"
 
 
-def flops(S, mode):
-    f = 4.0 * B * S * S * H * D
+def flops(S, mode, batch=None):
+    f = 4.0 * (B if batch is None else batch) * S * S * H * D
     return {"fwd": f, "bwd": 2.5 * f, "fwd_bwd": 3.5 * f}[mode]
 
 
@@ -207,11 +207,16 @@ def main():
         if rank == 0:
             print(json.dumps({"ring_check": "PASS" if fails == 0 else f"{fails} FAILED", "world": world}), flush=True)
 
-    runs = [(args.seq, args.causal)]
-    if args.configs:
-        runs = [(int(c.rstrip("c")), c.endswith("c")) for c in args.configs.split(",") if c]
-    for seq_i, causal_i in runs:
-        args.seq, args.causal = seq_i, causal_i
+    runs = [(args.seq, args.causal, B)]
+    if args.configs:  # "<seq>[c][b<batch>]", e.g. 262144, 524288c, 65536b4 (the reference README's two sweeps)
+        import re
+        runs = []
+        for c in args.configs.split(","):
+            m = re.fullmatch(r"(\d+)(c?)(?:b(\d+))?", c.strip())
+            assert m, f"bad config token {c!r}"
+            runs.append((int(m.group(1)), bool(m.group(2)), int(m.group(3) or B)))
+    for seq_i, causal_i, batch_i in runs:
+        args.seq, args.causal, args.batch = seq_i, causal_i, batch_i
         _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func)
         torch.cuda.empty_cache()
     if world > 1:
@@ -221,10 +226,11 @@ def main():
 
 def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
     S = args.seq
+    Bn = getattr(args, "batch", B)
     S_loc = S // world
     layout = "zigzag" if args.causal else "contiguous"
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    mk = lambda: torch.randn(B, S_loc, H, D, device=dev, generator=gen, dtype=torch.float32).to(torch.bfloat16)
+    mk = lambda: torch.randn(Bn, S_loc, H, D, device=dev, generator=gen, dtype=torch.float32).to(torch.bfloat16)
     q, k, v, do = mk(), mk(), mk(), mk()
 
     def step(qd, kd, vd, dod):
@@ -278,9 +284,9 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
     ms_fwd = timed(lambda: fwd_only(q, k, v), max(1, min(K, 3)))
 
     causal_div = 2.0 if args.causal else 1.0
-    fl_step = flops(S, "fwd_bwd") / causal_div
+    fl_step = flops(S, "fwd_bwd", Bn) / causal_div
     value = fl_step / (ms_step * 1e-3) / 1e12
-    fwd_tflops = flops(S, "fwd") / causal_div / (ms_fwd * 1e-3) / 1e12
+    fwd_tflops = flops(S, "fwd", Bn) / causal_div / (ms_fwd * 1e-3) / 1e12
 
     # ---- roofline of the dominant kernel (backward tile kernel: 2.5x the forward FLOPs)
     pk = peaks()
@@ -289,19 +295,19 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
         n_l, tot_ms = kms["bwd_chunk_kernel"]
         # algorithmic FLOPs per launch = this rank's share of the step's backward FLOPs (5 GEMMs:
         # 10*Sq*Sk*H*D per round) / launches per step; non-causal: exactly 10*S_loc^2*H*D per ring round
-        fl_launch = flops(S, "bwd") / causal_div / world / (n_l / K)
+        fl_launch = flops(S, "bwd", Bn) / causal_div / world / (n_l / K)
         ach = fl_launch / (tot_ms / n_l * 1e-3) / 1e12
         # DRAM traffic per launch from the committed ncu --set full capture (profiles/ncu_bwd_r01_final.txt:
         # dram__bytes_read 2.863 GB + write 1.771 GB) -- valid for the launch shape it was taken on
         # (Sq = Sk = 32768 per launch, H=32, non-causal: every multi-GPU ring round at S_local=32768)
-        traffic = 4.634e9 if (S_loc == 32768 and not args.causal and n_l == K * world) else None
+        traffic = 4.634e9 if (S_loc == 32768 and Bn == 1 and not args.causal and n_l == K * world) else None
         roof = {"kernel": "bwd_chunk_kernel", "bound": "tensor", "achieved": ach, "peak": pk["sustained"],
                 "unit": "TFLOP/s", "frac": ach / pk["sustained"], "traffic": traffic,
                 "peak_source": pk["source"] + " bf16_tflops_sustained (of measured)",
                 "launches": n_l, "avg_launch_ms": tot_ms / n_l}
         if "fwd_chunk_kernel" in kms:
             n_f, tot_f = kms["fwd_chunk_kernel"]
-            fl_f = flops(S, "fwd") / causal_div / world / (n_f / K)
+            fl_f = flops(S, "fwd", Bn) / causal_div / world / (n_f / K)
             roof["fwd_kernel"] = {"achieved": fl_f / (tot_f / n_f * 1e-3) / 1e12, "launches": n_f,
                                   "avg_launch_ms": tot_f / n_f,
                                   "frac": fl_f / (tot_f / n_f * 1e-3) / 1e12 / pk["sustained"]}
@@ -345,10 +351,10 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
             "metric": METRIC, "value": value, "unit": "TFLOPS/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": vs,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"burst_attn_func fwd+bwd, bs=1 S={S} (S_local={S_loc}) H=32 d=128 bf16 "
+            "config": {"workload": f"burst_attn_func fwd+bwd, bs={Bn} S={S} (S_local={S_loc}) H=32 d=128 bf16 "
                                    f"{'causal zigzag' if args.causal else 'non-causal contiguous'} shards, "
                                    f"{'local kernel, no ring' if world == 1 else f'{world}-rank ring over NCCL'}",
-                       "global_batch": B, "seq_len": S, "parallelism": f"sp{world}",
+                       "global_batch": Bn, "seq_len": S, "parallelism": f"sp{world}",
                        "l2": "inputs (>= 256 MiB per tensor per rank) exceed the 126 MB L2; no flush needed"},
             "value_per_gpu": value / world, "fwd_tflops": fwd_tflops, "fwd_ms": ms_fwd,
             "gpu_launches": int(tot_launch.item()), "clocks": clocks, "e2e": e2e, "roofline": roof, "overlap": overlap,
