@@ -176,7 +176,6 @@ def main():
     ap.add_argument("--configs", default="", help="comma list of extra runs in the same process group, e.g. "
                     "'262144,524288c,1048576' (c = causal zigzag); one JSON line each (multi-GPU sessions are "
                     "expensive to start)")
-    ap.add_argument("--ring-check", action="store_true", help="run tools/ring_check.py's parity cases first")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -199,13 +198,6 @@ def main():
     from burst_attn import chunk_ops, native
     native.check(native.lib().ba_device_check(), "ba_device_check")
     ops = chunk_ops.get_ops()
-
-    if args.ring_check and world > 1:
-        sys.path.insert(0, os.path.join(ROOT, "tools"))
-        import ring_check
-        fails = ring_check.run_cases(rank, world, dev)
-        if rank == 0:
-            print(json.dumps({"ring_check": "PASS" if fails == 0 else f"{fails} FAILED", "world": world}), flush=True)
 
     runs = [(args.seq, args.causal, B)]
     if args.configs:  # "<seq>[c][b<batch>]", e.g. 262144, 524288c, 65536b4 (the reference README's two sweeps)

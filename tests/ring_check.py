@@ -6,7 +6,7 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "burst-attention_b200")):
+for p in (ROOT, os.path.join(ROOT, "burst-attention_b200"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
@@ -24,6 +24,8 @@ def main():
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(1 if fails else 0)
+    # (to follow the parity cases with bench configurations in one expensive multi-GPU session, launch
+    #  bench.py --configs ... as a second torchrun command in the same gpurun call)
 
 
 def run_cases(rank, world, dev):

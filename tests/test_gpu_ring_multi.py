@@ -1,5 +1,5 @@
 """-m gpu, needs >= 2 GPUs on the box: the native NCCL ring + ring drivers, one
-process per GPU under torchrun, reference protocol (tools/ring_check.py)."""
+process per GPU under torchrun, reference protocol (tests/ring_check.py)."""
 import os
 import subprocess
 import sys
@@ -16,7 +16,7 @@ def test_ring_parity_all_visible_gpus():
     n = min(torch.cuda.device_count(), 8)
     n = 1 << (n.bit_length() - 1)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
-           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "ring_check.py")]
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "ring_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     sys.stdout.write(res.stdout[-4000:])
     sys.stderr.write(res.stderr[-4000:])
