@@ -119,7 +119,9 @@ int ba_ring_destroy(ba_ring* ring);
  * mode 0: S[128,128] fp32 = A[128,128] * B[128,128]^T through TMA + tcgen05 SS MMA
  * mode 1: O[128,128] fp32 = P[128,128] * V[128,128] with P staged in TMEM (TS MMA)
  * mode 2: raw dump of a TMA-loaded 128x64 SWIZZLE_128B box (16 KiB)
- * a, b: dtype [128,128] row-major; out: fp32 [128,128] (mode 2: 8192 x 16-bit). */
+ * mode 3: out = A^T * B with both operands MN-major (backward's dQ path)
+ * a, b: dtype [128,128] row-major; out: fp32 [128,128] (mode 2: 8192 x 16-bit).
+ * mode 4/5: CTA-pair (cta_group::2, cluster of 2) SS / TS GEMM: a [256,128], b [128,128], out fp32 [256,128]. */
 int ba_selftest(int mode, const void* a, const void* b, void* out, int dtype, void* stream);
 
 #ifdef __cplusplus

@@ -14,8 +14,10 @@ TOL = {torch.float16: dict(rtol=1e-3, atol=1e-2), torch.bfloat16: dict(rtol=1.6e
 
 
 def selftest(mode, a, b, out_dtype=torch.float32):
-    out = torch.zeros(128, 128, device=a.device, dtype=torch.float32) if mode != 2 else \
-        torch.zeros(8192, device=a.device, dtype=torch.int16)
+    if mode == 2:
+        out = torch.zeros(8192, device=a.device, dtype=torch.int16)
+    else:
+        out = torch.zeros(a.shape[0], 128, device=a.device, dtype=torch.float32)  # modes 4/5: a is [256,128]
     rc = nat.lib().ba_selftest(mode, a.data_ptr(), b.data_ptr(), out.data_ptr(), nat.dtype_code(a.dtype),
                                nat.stream_ptr(a.device))
     nat.check(rc, "ba_selftest")

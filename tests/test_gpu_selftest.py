@@ -45,3 +45,21 @@ def test_ss_mnmajor_gemm(ab):
     a, b = ab
     out = selftest(3, a, b)
     torch.testing.assert_close(out, a.float().t() @ b.float(), rtol=1e-3, atol=1e-2)
+
+
+def test_cta_pair_ss_gemm():
+    """cta_group::2: one M=256 MMA over a 2-CTA cluster, each CTA holding half of B (building block of the
+    planned CTA-pair kernels)."""
+    torch.manual_seed(1)
+    a = torch.randn(256, 128, device="cuda").to(torch.bfloat16)
+    b = torch.randn(128, 128, device="cuda").to(torch.bfloat16)
+    out = selftest(4, a, b)
+    torch.testing.assert_close(out, a.float() @ b.float().t(), rtol=1e-3, atol=1e-2)
+
+
+def test_cta_pair_ts_gemm():
+    torch.manual_seed(2)
+    a = torch.randn(256, 128, device="cuda").to(torch.bfloat16)
+    b = torch.randn(128, 128, device="cuda").to(torch.bfloat16)
+    out = selftest(5, a, b)
+    torch.testing.assert_close(out, a.float() @ b.float(), rtol=1e-3, atol=1e-2)
