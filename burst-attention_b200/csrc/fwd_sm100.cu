@@ -22,39 +22,11 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include "fwd_common.cuh"
 #include "host_common.h"
 #include "sm100_ptx.cuh"
 
 namespace ba {
-
-constexpr int kBlockM = 128;
-constexpr int kBlockN = 128;
-constexpr int kHeadDim = 128;
-constexpr int kKStages = 2;
-constexpr int kVStages = 2;
-constexpr int kTileBytes = kBlockN * kHeadDim * 2;  // 32 KiB: one 128x128 16-bit tile
-constexpr int kBoxBytes = kTileBytes / 2;           // 16 KiB: one 128 x 64 SW128 TMA box
-constexpr int kFwdThreads = 320;
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
-constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays <= 2^8
-
-struct FwdParams {
-  const uint16_t* q;  // raw 16-bit Q view (v3: rows are staged by the softmax threads into TMEM)
-  int64_t q_sb, q_ss, q_sh;
-  float* o_acc;
-  int64_t oacc_sb, oacc_ss, oacc_sh;
-  float* lse;
-  int64_t lse_sb, lse_sh;
-  void* o_out;
-  int64_t oout_sb, oout_ss, oout_sh;
-  int B, Sq, Sk, H;
-  float scale_log2;
-  int causal;
-  int causal_off;
-  int load_state;
-  int store_lowp;
-};
 
 struct __align__(8) FwdBarriers {
   uint64_t q_full;
@@ -1219,6 +1191,13 @@ extern "C" int ba_fwd_chunk(ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_tensor4
     const char* e = getenv("BA_FWD_IMPL");
     return e ? atoi(e) : 2;
   }();
+  if (impl == 5) {
+    BA_REQUIRE((reinterpret_cast<uintptr_t>(q.ptr) & 15) == 0 && q.stride_b % 8 == 0 && q.stride_s % 8 == 0 &&
+                   q.stride_h % 8 == 0, "ba_fwd_chunk: q must be a 16-byte aligned view");
+    CUtensorMap tmK64;
+    if ((rc = make_tensor_map(&tmK64, k, B, Sk, H, D, dt, 2, 64, 64, true))) return rc;
+    return launch_fwd_pair(dtype, tmK64, tmV, p, st);
+  }
   if (impl == 4)
     return dtype == BA_DTYPE_BF16 ? launch_fwd4<true>(tmQ, tmK, tmV, p, st) : launch_fwd4<false>(tmQ, tmK, tmV, p, st);
   if (impl == 3) {

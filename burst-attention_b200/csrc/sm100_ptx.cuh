@@ -364,6 +364,29 @@ BA_DEVICE void umma_ts_2cta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, u
       : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster (release at cluster scope)
+BA_DEVICE void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
+      :
+      : "r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+// lean (lo, hi) forms of the pair MMAs
+BA_DEVICE void umma_ts_2cta_lh(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                               uint32_t accumulate) {
+  if (elect_one())
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}\n"
+        :
+        : "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // MMA completion -> arrive on the barrier at this smem offset in BOTH CTAs (mask 0b11)
 BA_DEVICE void umma_commit_2cta(uint64_t* bar, uint16_t cta_mask) {
   if (elect_one()) asm volatile(
