@@ -11,6 +11,13 @@
 // warpgroups exchange row maxima / row sums through smem; warp 8 MMA issuer (leader CTA only issues),
 // warp 9 TMA producer (each CTA loads its halves; bytes complete on the leader's barriers).
 // Signals: MMA -> both CTAs by multicast tcgen05.commit; softmax -> leader by remote mbarrier arrive.
+//
+// STATUS (round 1): numerically correct on B200 for every forward test case (ragged, causal, fp16,
+// carried state), but only 775 TFLOP/s at S=16384 vs 1200 for the single-CTA kernel; a variant without
+// the per-tile inter-warpgroup exchange (full-row max per warpgroup, P single-buffered in the spare
+// TMEM columns) measured 686.  Not yet profiled -- the first item for the next round (ncu: leader issue
+// rate with 5 multicast commits per tile, remote-arrive latency of the 16-way p_ready, MUFU phases of
+// the two warpgroups running in lockstep).
 #include <math.h>
 
 #include "fwd_common.cuh"
@@ -26,7 +33,7 @@ constexpr uint32_t kPOffV = kPStages * kHalfBytes;
 constexpr uint32_t kPOffX = 2 * kPStages * kHalfBytes;  // fp32 [2][128] row-stat exchange
 constexpr uint32_t kPOffBars = kPOffX + 2 * 128 * 4;
 constexpr int kPairSmemBytes = kPOffBars + 512;
-constexpr uint32_t kTQ = 0, kTS0 = 64, kTO = 320, kTP = 448;  // TMEM columns (S_b at kTS0 + 128 b; P single-buffered)
+constexpr uint32_t kTQ = 0, kTS0 = 64, kTO = 320;       // TMEM columns (S_b at kTS0 + 128 b)
 
 struct __align__(8) PairBarriers {
   uint64_t k_full[kPStages], k_empty[kPStages];   // full: leader's copy collects both CTAs' bytes
@@ -61,8 +68,9 @@ __device__ __forceinline__ void pair_issue_pv(uint32_t sb16, uint32_t acc) {  //
   constexpr uint32_t idesc = make_idesc(kBF16, 256, kHeadDim, false, true), hi = desc_hi(1024);
   const uint32_t v_lo = sb16 + ((kPOffV + ST * kHalfBytes) >> 4) + desc_lo_lbo(kHalfBytes);
 #pragma unroll
-  for (int kk = 0; kk < kBlockN / 16; ++kk)  // P (16-bit, 128 keys) lives in its own columns [448,512)
-    umma_ts_2cta_lh(kTO, kTP + kk * 8, v_lo + kk * (16 * 128 / 16), hi, idesc, kk > 0 ? 1u : acc);
+  for (int kk = 0; kk < kBlockN / 16; ++kk)  // P: keys 0..63 at S_b cols [0,32), keys 64..127 at cols [64,96)
+    umma_ts_2cta_lh(kTO, kTS0 + B * 128 + (kk >> 2) * 64 + (kk & 3) * 8, v_lo + kk * (16 * 128 / 16), hi, idesc,
+                    kk > 0 ? 1u : acc);
 }
 
 // one tile of the leader's MMA warp; U = i % 4 (S buffer = U & 1, K/V stage = U) is compile-time
@@ -252,26 +260,12 @@ fwd_pair_kernel(const __grid_constant__ CUtensorMap tmK64, const __grid_constant
         mx2 = fmaxf(mx2, s[c + 2]);
         mx3 = fmaxf(mx3, s[c + 3]);
       }
-      // row maximum over all 128 keys: read the partner warpgroup's 64 S columns as well (TMEM reads are
-      // cheap; S is never overwritten by P any more, so no exchange / barrier between the warpgroups)
-      {
-        uint32_t so[64];
-        const uint32_t tSo = lane_base + kTS0 + bf * 128 + (g ^ 1) * 64;
-        tmem_ld_x32(tSo, so);
-        tmem_ld_x32(tSo + 32, so + 32);
-        tmem_wait_ld();
-        const float* o = reinterpret_cast<const float*>(so);
-        const int kb_o = i * kBlockN + (g ^ 1) * 64;
-        const bool need_mask = i * kBlockN + kBlockN - 1 > tile_min_limit;
-#pragma unroll
-        for (int c = 0; c < 64; c += 4) {
-          mx0 = fmaxf(mx0, (need_mask && kb_o + c > limit) ? -INFINITY : o[c]);
-          mx1 = fmaxf(mx1, (need_mask && kb_o + c + 1 > limit) ? -INFINITY : o[c + 1]);
-          mx2 = fmaxf(mx2, (need_mask && kb_o + c + 2 > limit) ? -INFINITY : o[c + 2]);
-          mx3 = fmaxf(mx3, (need_mask && kb_o + c + 3 > limit) ? -INFINITY : o[c + 3]);
-        }
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // row maximum over all 128 keys: exchange the two warpgroups' partial maxima through smem
+      const float mx_mine = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      sX[g * 128 + t] = mx_mine;
+      named_bar_sync(2, 256);
+      const float mx = fmaxf(mx_mine, sX[(g ^ 1) * 128 + t]);
+      named_bar_sync(3, 256);  // both have read before the next tile overwrites the slots
       const float m_new = fmaxf(m, mx * scale_log2);
       const bool grow = m_new > m + kRescaleThreshold;
       if (__any_sync(0xffffffffu, grow)) {  // same outcome in the partner warp (same rows, same m, same mx)
@@ -312,11 +306,7 @@ fwd_pair_kernel(const __grid_constant__ CUtensorMap tmK64, const __grid_constant
         pk[c / 2 + 1] = pack2<kBF16>(p2, p3);
       }
       l += (sum0 + sum1) + (sum2 + sum3);
-      if (i > 0) {  // the single P buffer is free once PV(i-1) has completed
-        mbar_wait(&bars->o_done, (i - 1) & 1);
-        tc_fence_after();
-      }
-      tmem_st_x32(lane_base + kTP + g * 32, pk);
+      tmem_st_x32(tS, pk);  // P (16-bit) over the first 32 of this warpgroup's own S columns
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
