@@ -40,4 +40,8 @@ struct FwdParams {
 int launch_fwd_pair(int dtype, const CUtensorMap& tmK64, const CUtensorMap& tmV, const FwdParams& p,
                     cudaStream_t stream);
 
+// second CTA-pair variant (independent even/odd key streams per warpgroup): opt-in, BA_FWD_IMPL=6
+int launch_fwd_pair6(int dtype, const CUtensorMap& tmQ, const CUtensorMap& tmK64, const CUtensorMap& tmV,
+                     const FwdParams& p, cudaStream_t stream);
+
 }  // namespace ba

@@ -1191,6 +1191,11 @@ extern "C" int ba_fwd_chunk(ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_tensor4
     const char* e = getenv("BA_FWD_IMPL");
     return e ? atoi(e) : 2;
   }();
+  if (impl == 6) {
+    CUtensorMap tmK64;
+    if ((rc = make_tensor_map(&tmK64, k, B, Sk, H, D, dt, 2, 64, 64, true))) return rc;
+    return launch_fwd_pair6(dtype, tmQ, tmK64, tmV, p, st);
+  }
   if (impl == 5) {
     BA_REQUIRE((reinterpret_cast<uintptr_t>(q.ptr) & 15) == 0 && q.stride_b % 8 == 0 && q.stride_s % 8 == 0 &&
                    q.stride_h % 8 == 0, "ba_fwd_chunk: q must be a 16-byte aligned view");
