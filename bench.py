@@ -256,7 +256,6 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
     # ---- warm-up (also builds the NCCL ring)
     for _ in range(W):
         step(q, k, v, do)
-    ops.launches = ops.launches  # (counter keeps running; deltas are taken around the timed region)
     torch.cuda.synchronize()
 
     # ---- timed: fwd+bwd, inputs resident in HBM; per-kernel events on the launching stream
