@@ -391,7 +391,8 @@ int launch_fwd_pair(int dtype, const CUtensorMap& tmK64, const CUtensorMap& tmV,
 
 
 // =====================================================================================================
-// Variant 6 (BA_FWD_IMPL=6; written at the end of round 1, NOT yet run on a GPU): same CTA pair, but the
+// Variant 6 (BA_FWD_IMPL=6; numerically correct on B200 on every forward diag case, 819 TFLOP/s at
+// S=16384 -- faster than variant 5 (775) but far from the single-CTA kernel (1200)): same CTA pair, but the
 // two softmax warpgroups of a CTA own DIFFERENT key tiles (even / odd) with their own O accumulator and
 // running (m, l), merged once in the epilogue -- so they never synchronise per tile and their MUFU
 // phases interleave (in variant 5 both warpgroups work on the same tile in lockstep: MUFU is saturated
