@@ -31,9 +31,45 @@ __all__ = ["burst_attn_func", "burst_attn_func_striped", "OpBurstAttn", "OpBurst
 
 
 def get_partition_id(double_group, r):
-    """Offset of the shard held in round ``r`` (reference :20-37).  The flat ring
-    used here is the ``double_group[0] is None`` branch: ``r - 1``."""
-    return r - 1
+    """Reference :20-37.  Single ring (``double_group[0] is None``): the OFFSET ``r - 1`` of the held shard
+    behind this rank.  Double ring: the RANK ID of the held shard, ``W = L*M``, rank ``= inter*L + intra``:
+    node ``(inter - (r-1)//L) mod M``, slot ``(intra - (r-1)%L) mod L`` (SURVEY.md Appendix C)."""
+    if double_group[0] is None:
+        return r - 1
+    L, M = get_world_size(double_group[0]), get_world_size(double_group[1])
+    b, a = get_rank(double_group[0]), get_rank(double_group[1])
+    return ((a - (r - 1) // L) % M) * L + (b - (r - 1) % L) % L
+
+
+class _Topology:
+    """Ring topology of one call: flat (one ring over ``process_group``) or hierarchical
+    (``double_group = [intra, inter]``, each optionally a ``(group, dq_group)`` pair, reference :188-194)."""
+
+    def __init__(self, process_group, double_group):
+        self.group = process_group
+        self.W, self.rank = get_world_size(process_group), get_rank(process_group)
+        intra, inter = double_group[0], double_group[1]
+        self.intra_dq = self.inter_dq = None
+        if isinstance(intra, (tuple, list)):
+            intra, self.intra_dq = intra
+        if isinstance(inter, (tuple, list)):
+            inter, self.inter_dq = inter
+        self.intra, self.inter = intra, inter
+        self.L, self.M = self.W, 1
+        self.hier = False
+        if intra is not None and inter is not None and os.environ.get("BA_DOUBLE_RING", "1") != "0":
+            L, M = get_world_size(intra), get_world_size(inter)
+            if 1 < L < self.W:  # reference comm.py:215-219: a ring that is all-intra (or all-inter) is flat
+                assert L * M == self.W, f"double ring: intra size {L} x inter size {M} != world {self.W}"
+                self.a, self.b = get_rank(inter), get_rank(intra)
+                assert self.a * L + self.b == self.rank, "double ring expects rank = inter_rank * intra_size + intra_rank"
+                self.L, self.M, self.hier = L, M, True
+
+    def source(self, r):
+        """Rank whose shard (K/V forward, Q-bundle backward) is held in round r (1-based)."""
+        if not self.hier:
+            return (self.rank - (r - 1)) % self.W
+        return get_partition_id([self.intra, self.inter], r)
 
 
 def split2_gethalf(inp, first_dim, half_idx=0):
@@ -118,13 +154,38 @@ def _check_inputs(q, k, v, seq_dim):
     assert q.dtype == k.dtype == v.dtype, "q, k, v must share a dtype"
 
 
+def _fwd_dispatch(ops, mode, r, W, i, j, q, cur_k, cur_v, o_acc, lse, out, scale, seq_dim):
+    """The kernel work of forward round r on rank i holding the K/V shard of rank j."""
+    first, last = r == 1, r == W
+    if mode == "none":
+        _fwd_round(ops, q, cur_k, cur_v, o_acc, lse, out, scale, False, 0, first, last, seq_dim)
+    elif mode == "zigzag":
+        if r == 1:  # own shard: plain causal (:221-224)
+            _fwd_round(ops, q, cur_k, cur_v, o_acc, lse, out, scale, True, 0, first, last, seq_dim)
+        elif j < i:  # split_kv: all Q x first half of K/V (:225-231)
+            _fwd_round(ops, q, _half(cur_k, seq_dim, 0), _half(cur_v, seq_dim, 0), o_acc, lse, out, scale,
+                       False, 0, False, last, seq_dim)
+        else:  # second half of Q x all K/V, merged into the second half of the state (:232-235)
+            _fwd_round(ops, _half(q, seq_dim, 1), cur_k, cur_v, _half(o_acc, seq_dim, 1), _half(lse, 2, 1),
+                       _half(out, seq_dim, 1), scale, False, 0, False, last, seq_dim)
+            if last:  # rows the last round did not visit: hand their finished state over
+                ops.cast(_half(o_acc, seq_dim, 0), _half(out, seq_dim, 0), seq_dim)
+    elif mode == "striped":
+        # source rank ahead of us -> strictly-lower-triangular (causal_shift, :454,:463-475)
+        _fwd_round(ops, q, cur_k, cur_v, o_acc, lse, out, scale, True, -1 if j > i else 0, first, last, seq_dim)
+    else:
+        raise ValueError(mode)
+
+
 # --------------------------------------------------------------------------- #
 # forward ring (reference OpBurstAttn.forward :171-253, OpBurstAttnStrip.forward :411-493)
 # --------------------------------------------------------------------------- #
-def _ring_forward(q, k, v, scale, seq_dim, mode, process_group):
+def _ring_forward(q, k, v, scale, seq_dim, mode, topo):
     """mode: "none" (non-causal) | "zigzag" | "striped".  Returns (out, lse[B,H,S] fp32)."""
+    if topo.hier:
+        return _ring_forward_hier(q, k, v, scale, seq_dim, mode, topo)
     ops = get_ops()
-    ring = Ring(process_group, tag="ring")
+    ring = Ring(topo.group, tag="ring")
     W, i = ring.world_size, ring.rank
     B, S, H = q.shape[0], q.shape[seq_dim], q.shape[3 - seq_dim]
     if mode == "zigzag":
@@ -138,42 +199,84 @@ def _ring_forward(q, k, v, scale, seq_dim, mode, process_group):
     recv = [[torch.empty_like(k), torch.empty_like(v)] for _ in range(min(2, W - 1))]
     cur_k, cur_v = k, v
     for r in range(1, W + 1):
-        j = (i - get_partition_id([None, None], r)) % W  # source rank of the held K/V (App. B)
+        j = topo.source(r)  # source rank of the held K/V (App. B)
         if r != W:
             nxt = recv[(r - 1) % len(recv)]
             ring.post([cur_k, cur_v], nxt)
-        first, last = r == 1, r == W
-        if mode == "none":
-            _fwd_round(ops, q, cur_k, cur_v, o_acc, lse, out, scale, False, 0, first, last, seq_dim)
-        elif mode == "zigzag":
-            if r == 1:  # own shard: plain causal (:221-224)
-                _fwd_round(ops, q, cur_k, cur_v, o_acc, lse, out, scale, True, 0, first, last, seq_dim)
-            elif j < i:  # split_kv: all Q x first half of K/V (:225-231)
-                _fwd_round(ops, q, _half(cur_k, seq_dim, 0), _half(cur_v, seq_dim, 0), o_acc, lse, out, scale,
-                           False, 0, False, last, seq_dim)
-            else:  # second half of Q x all K/V, merged into the second half of the state (:232-235)
-                _fwd_round(ops, _half(q, seq_dim, 1), cur_k, cur_v, _half(o_acc, seq_dim, 1), _half(lse, 2, 1),
-                           _half(out, seq_dim, 1), scale, False, 0, False, last, seq_dim)
-                if last:  # rows the last round did not visit: hand their finished state over
-                    ops.cast(_half(o_acc, seq_dim, 0), _half(out, seq_dim, 0), seq_dim)
-        elif mode == "striped":
-            # source rank ahead of us -> strictly-lower-triangular (causal_shift, :454,:463-475)
-            _fwd_round(ops, q, cur_k, cur_v, o_acc, lse, out, scale, True, -1 if j > i else 0, first, last, seq_dim)
-        else:
-            raise ValueError(mode)
+        _fwd_dispatch(ops, mode, r, W, i, j, q, cur_k, cur_v, o_acc, lse, out, scale, seq_dim)
         if r != W:
             ring.wait()
             cur_k, cur_v = nxt
     return out, lse
 
 
+def _ring_forward_hier(q, k, v, scale, seq_dim, mode, topo):
+    """Hierarchical ("double") ring, W = L*M (reference comm.py:187-254): rounds run
+    in M cycles of L steps.  Within a cycle K/V hop round the intra-node ring; the block a cycle starts
+    with is at the same time forwarded to the next node over the inter-node ring, where it starts the
+    following cycle -- a prefetch with L rounds of kernel time to hide behind.  Unlike the reference no
+    send-side copy is made: the cycle's starting block is never a receive target while it is in flight
+    (two inter-node buffers alternate)."""
+    ops = get_ops()
+    intra, inter = Ring(topo.intra, tag="ring"), Ring(topo.inter, tag="inter")
+    L, M, W, i = topo.L, topo.M, topo.W, topo.rank
+    B, S, H = q.shape[0], q.shape[seq_dim], q.shape[3 - seq_dim]
+    if mode == "zigzag":
+        assert S % 2 == 0, "zigzag causal sharding needs an even local sequence length"
+    out = torch.empty_like(q)
+    lse = torch.empty((B, H, S), dtype=torch.float32, device=q.device)
+    o_acc = torch.empty(q.shape, dtype=torch.float32, device=q.device)
+    k, v = k.contiguous(), v.contiguous()
+    recv = [[torch.empty_like(k), torch.empty_like(v)] for _ in range(min(2, L - 1))]
+    xbuf = [[torch.empty_like(k), torch.empty_like(v)] for _ in range(min(2, M - 1))]
+    cur = [k, v]
+    for r in range(1, W + 1):
+        c, t = divmod(r - 1, L)
+        j = topo.source(r)
+        if t == 0 and c != M - 1:  # next cycle's starting block, from the previous node
+            inter.post(cur, xbuf[c % len(xbuf)])
+        if t != L - 1:
+            nxt = recv[(r - 1) % len(recv)]
+            intra.post(cur, nxt)
+        _fwd_dispatch(ops, mode, r, W, i, j, q, cur[0], cur[1], o_acc, lse, out, scale, seq_dim)
+        if t != L - 1:
+            intra.wait()
+            cur = nxt
+        elif c != M - 1:
+            inter.wait()
+            cur = xbuf[c % len(xbuf)]
+    return out, lse
+
+
 # --------------------------------------------------------------------------- #
 # backward ring (reference OpBurstAttn.backward :256-398, OpBurstAttnStrip.backward :496-613)
 # --------------------------------------------------------------------------- #
-def _ring_backward(d_o, q, k, v, out, lse, scale, seq_dim, mode, process_group, deterministic):
+def _bwd_dispatch(ops, mode, r, i, j, bundle, dq_part, k, v, dk_acc, dv_acc, scale, seq_dim, deterministic):
+    """The kernel work of backward round r: K/V at home on rank i, Q-bundle of rank j."""
+    dlt, g, qq, ls = bundle
+    if mode == "none":
+        _bwd_round(ops, g, qq, k, v, dlt, ls, dq_part, dk_acc, dv_acc, scale, False, 0, seq_dim, deterministic)
+    elif mode == "zigzag":
+        if r == 1:
+            _bwd_round(ops, g, qq, k, v, dlt, ls, dq_part, dk_acc, dv_acc, scale, True, 0, seq_dim, deterministic)
+        elif j < i:  # split_q: second half of the bundle x all K/V (:322-345,:383-386)
+            _bwd_round(ops, _half(g, seq_dim, 1), _half(qq, seq_dim, 1), k, v, _half(dlt, 2, 1), _half(ls, 2, 1),
+                       _half(dq_part, seq_dim, 1), dk_acc, dv_acc, scale, False, 0, seq_dim, deterministic)
+        else:  # whole bundle x first half of K/V (:347-367,:387-390)
+            _bwd_round(ops, g, qq, _half(k, seq_dim, 0), _half(v, seq_dim, 0), dlt, ls, dq_part,
+                       _half(dk_acc, seq_dim, 0), _half(dv_acc, seq_dim, 0), scale, False, 0, seq_dim,
+                       deterministic)
+    elif mode == "striped":
+        # K/V home on i, bundle from j: strict iff j < i (causal_shift, :529)
+        _bwd_round(ops, g, qq, k, v, dlt, ls, dq_part, dk_acc, dv_acc, scale, True, -1 if j < i else 0, seq_dim,
+                   deterministic)
+    else:
+        raise ValueError(mode)
+
+
+def _ring_backward(d_o, q, k, v, out, lse, scale, seq_dim, mode, topo, deterministic):
     ops = get_ops()
-    ring = Ring(process_group, tag="ring")
-    W, i = ring.world_size, ring.rank
+    W, i = topo.W, topo.rank
     dev = q.device
     q, k, v, d_o, out = (t.contiguous() for t in (q, k, v, d_o, out))
     B, S, H = q.shape[0], q.shape[seq_dim], q.shape[3 - seq_dim]
@@ -189,36 +292,21 @@ def _ring_backward(d_o, q, k, v, out, lse, scale, seq_dim, mode, process_group, 
     part = torch.zeros(q.shape, **f32)  # this round's dQ partial (the kernel reduce-adds into it)
 
     def round_kernel(r, j, bundle, dq_part):
-        dlt, g, qq, ls = bundle
-        if mode == "none":
-            _bwd_round(ops, g, qq, k, v, dlt, ls, dq_part, dk_acc, dv_acc, scale, False, 0, seq_dim, deterministic)
-        elif mode == "zigzag":
-            if r == 1:
-                _bwd_round(ops, g, qq, k, v, dlt, ls, dq_part, dk_acc, dv_acc, scale, True, 0, seq_dim, deterministic)
-            elif j < i:  # split_q: second half of the bundle x all K/V (:322-345,:383-386)
-                _bwd_round(ops, _half(g, seq_dim, 1), _half(qq, seq_dim, 1), k, v, _half(dlt, 2, 1), _half(ls, 2, 1),
-                           _half(dq_part, seq_dim, 1), dk_acc, dv_acc, scale, False, 0, seq_dim, deterministic)
-            else:  # whole bundle x first half of K/V (:347-367,:387-390)
-                _bwd_round(ops, g, qq, _half(k, seq_dim, 0), _half(v, seq_dim, 0), dlt, ls, dq_part,
-                           _half(dk_acc, seq_dim, 0), _half(dv_acc, seq_dim, 0), scale, False, 0, seq_dim,
-                           deterministic)
-        elif mode == "striped":
-            # K/V home on i, bundle from j: strict iff j < i (causal_shift, :529)
-            _bwd_round(ops, g, qq, k, v, dlt, ls, dq_part, dk_acc, dv_acc, scale, True, -1 if j < i else 0, seq_dim,
-                       deterministic)
-        else:
-            raise ValueError(mode)
+        _bwd_dispatch(ops, mode, r, i, j, bundle, dq_part, k, v, dk_acc, dv_acc, scale, seq_dim, deterministic)
 
     bundle = [delta, d_o, q, lse.contiguous()]
     if W == 1:
         round_kernel(1, i, bundle, part)
         dq_final = part
+    elif topo.hier:
+        dq_final = _bwd_rounds_hier(ops, topo, round_kernel, bundle, part, q.shape, f32, seq_dim)
     else:
+        ring = Ring(topo.group, tag="ring")
         recv = [[torch.empty_like(t) for t in bundle] for _ in range(min(2, W - 1))]
         hold = None                      # fp32 dQ accumulated for the bundle held in the previous round
         spare = [torch.empty(q.shape, **f32), torch.empty(q.shape, **f32)]
         for r in range(1, W + 1):
-            j = (i - get_partition_id([None, None], r)) % W
+            j = topo.source(r)
             srcs: List[torch.Tensor] = []
             dsts: List[torch.Tensor] = []
             if r != W:  # bundle hop (:295-299)
@@ -259,11 +347,94 @@ def _ring_backward(d_o, q, k, v, out, lse, scale, seq_dim, mode, process_group, 
     return dq, dk, dv
 
 
+def _bwd_rounds_hier(ops, topo, round_kernel, bundle, part, qshape, f32, seq_dim):
+    """Backward rounds over the hierarchical ring (W = L*M); returns the fp32 dQ of this rank's own rows.
+
+    The Q-bundle travels exactly like K/V in the forward (intra-node hops inside a cycle, the cycle's
+    starting bundle prefetched to the next node).  Its dQ comes home in two levels (the reference's
+    ``double_ring_send_recv_q``, comm.py:187-213, restated):
+      * inside a cycle the partial rides one intra-node hop behind its bundle and picks up each rank's
+        contribution (as in the flat ring); one more intra-node hop after the cycle's last step closes the
+        ring, so the NODE sum for a bundle lands on the rank that started it in this node;
+      * node sums chain along the inter-node ring: at the start of cycle c the node sum of the bundle
+        started in cycle c-1 is added to the running sum received from the previous node and sent on --
+        L rounds of kernel time to hide behind.  After the last cycle the same step is the hop home.
+    """
+    L, M, W = topo.L, topo.M, topo.W
+    intra = Ring(topo.intra, tag="ring")
+    inter = Ring(topo.inter, tag="inter")
+    inter_q = Ring(topo.inter_dq if topo.inter_dq is not None else topo.inter, tag="inter_dq")
+    recv = [[torch.empty_like(t) for t in bundle] for _ in range(min(2, L - 1))]
+    xbuf = [[torch.empty_like(t) for t in bundle] for _ in range(min(2, M - 1))]
+    free: List[torch.Tensor] = []
+
+    def take():
+        return free.pop() if free else torch.empty(qshape, **f32)
+
+    hold = None      # dQ accumulated in this node for the bundle held in the previous round
+    running = None   # inter-node running sum in flight to the next node (kept alive until awaited)
+    inter_in = None  # running sum arriving from the previous node
+
+    def chain(node_sum):
+        """node_sum (+ the sum received from the previous node) -> next node; returns the receive buffer."""
+        nonlocal running, inter_in
+        if inter_in is not None:
+            inter_q.wait()
+            ops.accumulate(inter_in, node_sum, seq_dim)
+            free.extend([inter_in, running])
+        running, inter_in = node_sum, take()
+        inter_q.post([running], [inter_in])
+
+    for r in range(1, W + 1):
+        c, t = divmod(r - 1, L)
+        j = topo.source(r)
+        srcs: List[torch.Tensor] = []
+        dsts: List[torch.Tensor] = []
+        inbound = None
+        if t != L - 1:  # bundle hop inside the node
+            nxt = recv[(r - 1) % len(recv)]
+            srcs += bundle
+            dsts += nxt
+        if r != 1:  # dQ hop: behind its bundle (t > 0), or closing the previous cycle's ring (t == 0)
+            inbound = take()
+            srcs.append(hold)
+            dsts.append(inbound)
+        if srcs:
+            intra.post(srcs, dsts)
+        if t == 0 and c != M - 1:  # next cycle's starting bundle, from the previous node
+            inter.post(bundle, xbuf[c % len(xbuf)])
+        round_kernel(r, j, bundle, part)
+        if srcs:
+            intra.wait()
+        if t == 0:
+            if r != 1:
+                free.append(hold)
+                chain(inbound)  # inbound = node sum of the bundle this rank started one cycle ago
+            hold, part = part, take()
+            part.zero_()
+        else:
+            ops.accumulate(part, inbound, seq_dim)
+            free.append(hold)
+            hold = inbound
+            if r != W:
+                part.zero_()
+        if t != L - 1:
+            bundle = nxt
+        elif c != M - 1:
+            inter.wait()
+            bundle = xbuf[c % len(xbuf)]
+    # close the last cycle's intra-node ring, then the last inter-node hop is the hop home (:393-396)
+    node_sum = take()
+    intra.post([hold], [node_sum])
+    intra.wait()
+    chain(node_sum)
+    inter_q.wait()
+    return inter_in
+
+
 # --------------------------------------------------------------------------- #
 def _prepare(ctx, q, k, v, softmax_scale, flash, causal, optimize_bwd_comm, deterministic, process_group,
              double_group):
-    if isinstance(double_group[0], tuple):  # (group, dq_group) pairs (:188-194): one flat ring serves both
-        double_group = (double_group[0][0], double_group[1][0])
     assert not causal or flash == "cuda", "Causal attention only supported for Flash v2"
     ctx.softmax_scale = 1 / math.sqrt(q.shape[-1]) if softmax_scale is None else softmax_scale
     ctx.flash = None if flash not in ["cuda", "triton"] else flash
@@ -273,6 +444,7 @@ def _prepare(ctx, q, k, v, softmax_scale, flash, causal, optimize_bwd_comm, dete
     ctx.deterministic = deterministic
     ctx.process_group = process_group
     ctx.double_group = double_group
+    ctx.topo = _Topology(process_group, double_group)
     _check_inputs(q, k, v, ctx.seq_dim)
 
 
@@ -290,7 +462,7 @@ class OpBurstAttn(torch.autograd.Function):
         _prepare(ctx, q, k, v, softmax_scale, flash, causal, optimize_bwd_comm, deterministic, process_group,
                  double_group)
         ctx.mode = "zigzag" if causal else "none"
-        out, lse = _ring_forward(q, k, v, ctx.softmax_scale, ctx.seq_dim, ctx.mode, process_group)
+        out, lse = _ring_forward(q, k, v, ctx.softmax_scale, ctx.seq_dim, ctx.mode, ctx.topo)
         ctx.save_for_backward(q, k, v, lse, out)
         return out
 
@@ -298,7 +470,7 @@ class OpBurstAttn(torch.autograd.Function):
     def backward(ctx, grad_output):
         q, k, v, lse, out = ctx.saved_tensors
         dq, dk, dv = _ring_backward(grad_output, q, k, v, out, lse, ctx.softmax_scale, ctx.seq_dim, ctx.mode,
-                                    ctx.process_group, ctx.deterministic)
+                                    ctx.topo, ctx.deterministic)
         return dq, dk, dv, None, None, None, None, None, None, None
 
 
@@ -311,7 +483,7 @@ class OpBurstAttnStrip(torch.autograd.Function):
         _prepare(ctx, q, k, v, softmax_scale, flash, causal, optimize_bwd_comm, deterministic, process_group,
                  double_group)
         ctx.mode = "striped" if causal else "none"
-        out, lse = _ring_forward(q, k, v, ctx.softmax_scale, ctx.seq_dim, ctx.mode, process_group)
+        out, lse = _ring_forward(q, k, v, ctx.softmax_scale, ctx.seq_dim, ctx.mode, ctx.topo)
         ctx.save_for_backward(q, k, v, lse, out)
         return out
 
@@ -319,7 +491,7 @@ class OpBurstAttnStrip(torch.autograd.Function):
     def backward(ctx, grad_output):
         q, k, v, lse, out = ctx.saved_tensors
         dq, dk, dv = _ring_backward(grad_output, q, k, v, out, lse, ctx.softmax_scale, ctx.seq_dim, ctx.mode,
-                                    ctx.process_group, ctx.deterministic)
+                                    ctx.topo, ctx.deterministic)
         return dq, dk, dv, None, None, None, None, None, None, None
 
 

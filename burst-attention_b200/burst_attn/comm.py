@@ -13,10 +13,14 @@ awaited by ``wait``.  Two transports:
 * ``torch`` (CPU tensors under gloo, used by the world_size-2 CPU tests of the
   ring schedule): ``dist.batch_isend_irecv`` as in comm.py:159-171,269.
 
-8 x B200 on one NVSwitch is a uniform fabric, so the intra/inter "double ring"
-(comm.py:187-254) is not needed; ``double_group`` is accepted and served by the
-flat ring over ``process_group`` (same results: only the summation order of the
-rounds changes).
+A ``Ring`` here is always ONE ring over ONE group.  The reference's intra/inter
+"double ring" (comm.py:187-254) is composed by the drivers from up to three of
+them -- intra-node hops, inter-node prefetch of the block that starts the next
+cycle, inter-node chain of the dQ node sums (burst_attn_interface.py:
+``_ring_forward_hier`` / ``_bwd_rounds_hier``) -- so each level has its own
+communicator and side stream and is awaited independently.  8 x B200 on one
+NVSwitch is a uniform fabric where the flat ring is as good; the hierarchy is for
+W spanning several NVLink domains.
 """
 from __future__ import annotations
 
@@ -105,7 +109,7 @@ class Ring:
         self.world_size = get_world_size(process_group)
         self.rank = get_rank(process_group)
         self.tag = tag or ("dq" if dq else "kv")
-        # double-ring bookkeeping kept for API compatibility (comm.py:137-141)
+        # reference field names kept for API compatibility (comm.py:137-141); hierarchy lives in the drivers
         self.local_group, self.local_group2 = local_group[0], local_group[1]
         self.double_ring = False
         self.intra_size = self.world_size

@@ -28,9 +28,32 @@ def main():
     #  bench.py --configs ... as a second torchrun command in the same gpurun call)
 
 
+def _double_group(world, intra):
+    """[(intra, intra_dq), (inter, inter_dq)] as the reference's get_group builds them (test_burst.py:120-156)."""
+    rows = [list(range(n * intra, (n + 1) * intra)) for n in range(world // intra)]
+    cols = [list(c) for c in zip(*rows)]
+    mk = lambda ranks: dist.new_subgroups_by_enumeration(ranks, backend="nccl")[0]  # noqa: E731
+    return [(mk(rows), mk(rows)), (mk(cols), mk(cols))]
+
+
 def run_cases(rank, world, dev):
     n_heads = int(os.environ.get("RING_CHECK_HEADS", "8"))
     fails = 0
+    # RING_CHECK_DOUBLE=<intra size>: run every case over the hierarchical (double) ring as well.  Opt-in:
+    # that schedule is covered by the gloo tests (tests/test_ring_gloo.py); its NCCL transport has not yet
+    # had a multi-GPU session (DESIGN.md 5).
+    intra = int(os.environ.get("RING_CHECK_DOUBLE", "0"))
+    double_group = _double_group(world, intra) if intra and world % intra == 0 and 1 < intra < world else None
+    for dg in ([None, None], double_group):
+        if dg is None:
+            continue
+        fails += _run_cases(rank, world, dev, n_heads, dg)
+    return fails
+
+
+def _run_cases(rank, world, dev, n_heads, double_group):
+    fails = 0
+    tag = "double" if double_group[0] is not None else "flat"
     for dtype, tol in ((torch.float16, dict(rtol=1e-3, atol=1e-2)), (torch.bfloat16, dict(rtol=1.6e-2, atol=2e-2))):
         for name, func, causal, layout in (("none", burst_attn_func, False, "contiguous"),
                                            ("zigzag", burst_attn_func, True, "zigzag"),
@@ -42,7 +65,7 @@ def run_cases(rank, world, dev):
             sh = lambda t: orc.shard(t, rank, world, layout).to(dev)
             ql, kl, vl = (sh(t).requires_grad_() for t in (q, k, v))
             k_before = kl.detach().clone()
-            o = func(ql, kl, vl, None, "cuda", causal, True, False, None)
+            o = func(ql, kl, vl, None, "cuda", causal, True, False, None, double_group)
             dq, dk, dv = torch.autograd.grad(o, (ql, kl, vl), sh(do))
             torch.cuda.synchronize()
             ok = True
@@ -59,7 +82,7 @@ def run_cases(rank, world, dev):
             flag = torch.tensor([0 if ok else 1], device=dev)
             dist.all_reduce(flag)
             if rank == 0:
-                print(f"ring_check W={world} {name:8s} {str(dtype):15s} {'PASS' if flag.item() == 0 else 'FAIL'}", flush=True)
+                print(f"ring_check W={world} {tag:6s} {name:8s} {str(dtype):15s} {'PASS' if flag.item() == 0 else 'FAIL'}", flush=True)
             fails += int(flag.item())
     return fails
 

@@ -24,7 +24,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, case, seq_dim, errq):
+def _worker(rank, world, port, case, seq_dim, errq, intra=0, dq_groups=False):
     try:
         for p in (ROOT, os.path.join(ROOT, "burst-attention_b200"), os.path.join(ROOT, "tests")):
             if p not in sys.path:
@@ -62,7 +62,25 @@ def _worker(rank, world, port, case, seq_dim, errq):
         flash = "cuda" if seq_dim == 1 else None
         if causal and seq_dim == 2:
             return  # reference asserts causal needs flash == "cuda"
-        o = func(ql, kl, vl, None, flash, causal, True, False, None)
+        double_group = [None, None]
+        if intra:  # hierarchical ring: nodes of `intra` consecutive ranks (reference test/test_burst.py:120-156)
+            rows = [list(range(n * intra, (n + 1) * intra)) for n in range(world // intra)]
+            cols = [list(c) for c in zip(*rows)]
+            mk = lambda ranks: dist.new_subgroups_by_enumeration(ranks, backend="gloo")[0]  # noqa: E731
+            double_group = [mk(rows), mk(cols)]
+            if dq_groups:
+                double_group = [(double_group[0], mk(rows)), (double_group[1], mk(cols))]
+            from burst_attn.burst_attn_interface import _Topology, get_partition_id
+            topo = _Topology(None, double_group)
+            assert topo.hier and (topo.L, topo.M) == (intra, world // intra)
+            plain = [g[0] if isinstance(g, tuple) else g for g in double_group]
+            seen = sorted(get_partition_id(plain, r) for r in range(1, world + 1))
+            assert seen == list(range(world)), seen  # every shard is visited exactly once
+            assert get_partition_id(plain, 1) == rank
+            for r in range(1, world + 1):  # the oracle's restatement is pinned to the reference (tests/golden)
+                assert get_partition_id(plain, r) == orc.get_partition_id_double(r, rank % intra, rank // intra, intra,
+                                                                                world // intra)
+        o = func(ql, kl, vl, None, flash, causal, True, False, None, double_group)
         g = torch.autograd.grad(o, (ql, kl, vl), sh(do))
         tol = dict(rtol=1e-5, atol=1e-5)  # fp32 carried state / accumulators in the driver
         torch.testing.assert_close(unlay(o.detach()), orc.shard(o_ref.detach(), rank, world, layout), **tol)
@@ -94,6 +112,29 @@ def test_ring_driver_matches_dense(world, case):
         p.start()
     for p in procs:
         p.join(180)
+    errs = []
+    while not errq.empty():
+        errs.append(errq.get())
+    assert not errs, "\n".join(errs)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+
+
+@pytest.mark.parametrize("world,intra,case,dq_groups", [
+    (4, 2, "none", False), (4, 2, "zigzag", True), (4, 2, "striped", False),
+    (6, 3, "zigzag", False), (6, 2, "none", True), (6, 2, "striped", False),
+])
+def test_double_ring_matches_dense(world, intra, case, dq_groups):
+    """Hierarchical (double) ring, W = L*M with (L, M) in {(2,2), (3,2), (2,3)}: K/V and Q-bundle prefetch
+    across nodes, dQ node sums chained along the inter-node ring (reference test_burst.py:239-247
+    ``double_ring`` axis)."""
+    ctx = mp.get_context("spawn")
+    errq = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, 1, errq, intra, dq_groups)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
     errs = []
     while not errq.empty():
         errs.append(errq.get())
