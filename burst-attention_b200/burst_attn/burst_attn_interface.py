@@ -448,6 +448,40 @@ def _prepare(ctx, q, k, v, softmax_scale, flash, causal, optimize_bwd_comm, dete
     _check_inputs(q, k, v, ctx.seq_dim)
 
 
+def _pad_head_dim(ops, tensors):
+    """The sm_100a tile kernels are built for head_dim 128 (``ops.tile_head_dim``).  A smaller head_dim
+    (the reference's CPU-runnable configuration C1 has 64) is run exactly by zero-padding the last axis
+    once per call: padded Q/K columns add 0 to every score, padded V columns produce output columns that
+    are exactly 0 and are sliced off, and the same holds for dO -> dQ/dK/dV.  Costs one copy per tensor
+    and runs the tile at D/128 of its efficiency; a native 64-wide tile is future work."""
+    tile = getattr(ops, "tile_head_dim", None)
+    D = tensors[0].shape[-1]
+    if tile is None or D == tile:
+        return tensors, D
+    assert D < tile, f"head_dim {D} > {tile} is not supported"
+    return [torch.nn.functional.pad(t, (0, tile - D)) for t in tensors], D
+
+
+def _unpad(t, D):
+    return t if t.shape[-1] == D else t[..., :D].contiguous()
+
+
+def _op_forward(ctx, q, k, v, mode):
+    (qp, kp, vp), ctx.head_dim = _pad_head_dim(get_ops(), [q, k, v])
+    out, lse = _ring_forward(qp, kp, vp, ctx.softmax_scale, ctx.seq_dim, mode, ctx.topo)
+    ctx.mode = mode
+    ctx.save_for_backward(qp, kp, vp, lse, out)
+    return _unpad(out, ctx.head_dim)
+
+
+def _op_backward(ctx, grad_output):
+    q, k, v, lse, out = ctx.saved_tensors
+    (g,), _ = _pad_head_dim(get_ops(), [grad_output])
+    dq, dk, dv = _ring_backward(g, q, k, v, out, lse, ctx.softmax_scale, ctx.seq_dim, ctx.mode, ctx.topo,
+                                ctx.deterministic)
+    return tuple(_unpad(t, ctx.head_dim) for t in (dq, dk, dv)) + (None,) * 7
+
+
 class OpBurstAttn(torch.autograd.Function):
     """
     for Normal Attention (flash=None):  q, k, v: [B, N, S, H]
@@ -461,17 +495,11 @@ class OpBurstAttn(torch.autograd.Function):
                 deterministic=False, process_group=None, double_group=[None, None]):
         _prepare(ctx, q, k, v, softmax_scale, flash, causal, optimize_bwd_comm, deterministic, process_group,
                  double_group)
-        ctx.mode = "zigzag" if causal else "none"
-        out, lse = _ring_forward(q, k, v, ctx.softmax_scale, ctx.seq_dim, ctx.mode, ctx.topo)
-        ctx.save_for_backward(q, k, v, lse, out)
-        return out
+        return _op_forward(ctx, q, k, v, "zigzag" if causal else "none")
 
     @staticmethod
     def backward(ctx, grad_output):
-        q, k, v, lse, out = ctx.saved_tensors
-        dq, dk, dv = _ring_backward(grad_output, q, k, v, out, lse, ctx.softmax_scale, ctx.seq_dim, ctx.mode,
-                                    ctx.topo, ctx.deterministic)
-        return dq, dk, dv, None, None, None, None, None, None, None
+        return _op_backward(ctx, grad_output)
 
 
 class OpBurstAttnStrip(torch.autograd.Function):
@@ -482,17 +510,11 @@ class OpBurstAttnStrip(torch.autograd.Function):
                 deterministic=False, process_group=None, double_group=[None, None]):
         _prepare(ctx, q, k, v, softmax_scale, flash, causal, optimize_bwd_comm, deterministic, process_group,
                  double_group)
-        ctx.mode = "striped" if causal else "none"
-        out, lse = _ring_forward(q, k, v, ctx.softmax_scale, ctx.seq_dim, ctx.mode, ctx.topo)
-        ctx.save_for_backward(q, k, v, lse, out)
-        return out
+        return _op_forward(ctx, q, k, v, "striped" if causal else "none")
 
     @staticmethod
     def backward(ctx, grad_output):
-        q, k, v, lse, out = ctx.saved_tensors
-        dq, dk, dv = _ring_backward(grad_output, q, k, v, out, lse, ctx.softmax_scale, ctx.seq_dim, ctx.mode,
-                                    ctx.topo, ctx.deterministic)
-        return dq, dk, dv, None, None, None, None, None, None, None
+        return _op_backward(ctx, grad_output)
 
 
 def burst_attn_func_striped(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, softmax_scale: float = None,

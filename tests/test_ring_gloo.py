@@ -180,6 +180,44 @@ def test_single_process_world1_cpu():
         chunk_ops._set_ops_for_testing(None)
 
 
+def test_head_dim_padding_world1_cpu():
+    """head_dim below the tile's (128 on the GPU; 32 faked here) is zero-padded once per call by the
+    driver and sliced off again -- exact for O, dQ, dK, dV, both layouts."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from burst_attn import burst_attn_func, burst_attn_func_striped, chunk_ops
+    from oracle import attention_oracle as orc
+    from oracle_ops import OracleOps
+    ops = OracleOps()
+    ops.tile_head_dim = 32
+    chunk_ops._set_ops_for_testing(ops)
+    try:
+        torch.manual_seed(5)
+        q, k, v, do = (torch.randn(2, 40, 3, 16, dtype=torch.float64) for _ in range(4))
+        for func, causal in ((burst_attn_func, False), (burst_attn_func, True), (burst_attn_func_striped, True)):
+            ops.calls.clear()
+            qq, kk, vv = (t.clone().requires_grad_() for t in (q, k, v))
+            o = func(qq, kk, vv, None, "cuda", causal)
+            assert o.shape == q.shape and o.is_contiguous()
+            g = torch.autograd.grad(o, (qq, kk, vv), do)
+            assert all(c[1][-1] == 32 for c in ops.calls if c[0] in ("fwd", "bwd"))  # the tile saw padded heads
+            o_ref, _, dq, dk, dv = orc.dense_attention_bwd(q, k, v, do, None, causal)
+            torch.testing.assert_close(o.detach(), o_ref, rtol=1e-5, atol=1e-5)
+            for a, b in zip(g, (dq, dk, dv)):
+                assert a.shape == b.shape
+                torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5)
+        # normal layout [B, H, S, D]
+        p = lambda t: t.permute(0, 2, 1, 3).contiguous()  # noqa: E731
+        qq, kk, vv = (p(t).requires_grad_() for t in (q, k, v))
+        o = burst_attn_func(qq, kk, vv, None, None, False)
+        g = torch.autograd.grad(o, (qq, kk, vv), p(do))
+        o_ref, _, dq, dk, dv = orc.dense_attention_bwd(q, k, v, do, None, False)
+        torch.testing.assert_close(o.detach(), p(o_ref), rtol=1e-5, atol=1e-5)
+        for a, b in zip(g, (dq, dk, dv)):
+            torch.testing.assert_close(a, p(b), rtol=1e-5, atol=1e-5)
+    finally:
+        chunk_ops._set_ops_for_testing(None)
+
+
 @pytest.mark.parametrize("blk", [16, 24])
 def test_l2_blocking_of_rounds_matches_dense(monkeypatch, blk):
     """The driver splits a round into L2-sized sub-launches (carried state forward, row blocks backward,
