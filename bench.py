@@ -176,6 +176,9 @@ def main():
     ap.add_argument("--configs", default="", help="comma list of extra runs in the same process group, e.g. "
                     "'262144,524288c,1048576' (c = causal zigzag); one JSON line each (multi-GPU sessions are "
                     "expensive to start)")
+    ap.add_argument("--double-ring", type=int, default=0, metavar="L",
+                    help="run over the hierarchical (double) ring with intra-node rings of L consecutive ranks "
+                         "(reference benchmarks/benchmark.py --double_ring); default 0 = flat ring")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -198,6 +201,14 @@ def main():
     from burst_attn import chunk_ops, native
     native.check(native.lib().ba_device_check(), "ba_device_check")
     ops = chunk_ops.get_ops()
+
+    args.double_group = [None, None]
+    if args.double_ring and world > 1:
+        L = args.double_ring
+        assert world % L == 0 and 1 < L < world, "--double-ring L needs 1 < L < world and L | world"
+        rows = [list(range(n * L, (n + 1) * L)) for n in range(world // L)]
+        mk_groups = lambda ranks: dist.new_subgroups_by_enumeration(ranks, backend="nccl")[0]  # noqa: E731
+        args.double_group = [mk_groups(rows), mk_groups([list(c) for c in zip(*rows)])]
 
     runs = [(args.seq, args.causal, B)]
     if args.configs:  # "<seq>[c][b<batch>]", e.g. 262144, 524288c, 65536b4 (the reference README's two sweeps)
@@ -227,13 +238,13 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
 
     def step(qd, kd, vd, dod):
         qq, kk, vv = qd.detach().requires_grad_(), kd.detach().requires_grad_(), vd.detach().requires_grad_()
-        o = burst_attn_func(qq, kk, vv, None, "cuda", args.causal, True, False, None)
+        o = burst_attn_func(qq, kk, vv, None, "cuda", args.causal, True, False, None, args.double_group)
         dq, dk, dv = torch.autograd.grad(o, (qq, kk, vv), dod)
         return o, dq, dk, dv
 
     def fwd_only(qd, kd, vd):
         with torch.no_grad():
-            return burst_attn_func(qd, kd, vd, None, "cuda", args.causal, True, False, None)
+            return burst_attn_func(qd, kd, vd, None, "cuda", args.causal, True, False, None, args.double_group)
 
     def barrier():
         if world > 1:
@@ -344,7 +355,8 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"burst_attn_func fwd+bwd, bs={Bn} S={S} (S_local={S_loc}) H=32 d=128 bf16 "
                                    f"{'causal zigzag' if args.causal else 'non-causal contiguous'} shards, "
-                                   f"{'local kernel, no ring' if world == 1 else f'{world}-rank ring over NCCL'}",
+                                   f"{'local kernel, no ring' if world == 1 else f'{world}-rank ring over NCCL'}"
+                                   f"{f' (double ring, intra {args.double_ring})' if args.double_ring and world > 1 else ''}",
                        "global_batch": Bn, "seq_len": S, "parallelism": f"sp{world}",
                        "l2": "inputs (>= 256 MiB per tensor per rank) exceed the 126 MB L2; no flush needed"},
             "value_per_gpu": value / world, "fwd_tflops": fwd_tflops, "fwd_ms": ms_fwd,
