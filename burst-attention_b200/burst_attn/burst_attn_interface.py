@@ -84,6 +84,10 @@ def _half(t, dim, idx):
     return t.narrow(dim, 0, n) if idx == 0 else t.narrow(dim, n, t.shape[dim] - n)
 
 
+def _nbytes(t) -> int:
+    return t.numel() * t.element_size()
+
+
 def _l2_block() -> int:
     """Rows/keys per sub-launch.  One (batch, head) slice of 32768 keys is 16 MiB of K+V (or 32 MiB of
     Q, dO and fp32 dQ in the backward), so the streamed operands of a launch stay resident in B200's
@@ -196,7 +200,8 @@ def _ring_forward(q, k, v, scale, seq_dim, mode, topo):
     o_acc = torch.empty(q.shape, dtype=torch.float32, device=q.device) if need_state else None
     if W > 1:
         k, v = k.contiguous(), v.contiguous()
-    recv = [[torch.empty_like(k), torch.empty_like(v)] for _ in range(min(2, W - 1))]
+    ring.begin(q, [_nbytes(k), _nbytes(v)] * min(2, W - 1))
+    recv = [[ring.empty_like(k), ring.empty_like(v)] for _ in range(min(2, W - 1))]
     cur_k, cur_v = k, v
     for r in range(1, W + 1):
         j = topo.source(r)  # source rank of the held K/V (App. B)
@@ -218,7 +223,8 @@ def _ring_forward_hier(q, k, v, scale, seq_dim, mode, topo):
     send-side copy is made: the cycle's starting block is never a receive target while it is in flight
     (two inter-node buffers alternate)."""
     ops = get_ops()
-    intra, inter = Ring(topo.intra, tag="ring"), Ring(topo.inter, tag="inter")
+    # (the copy-engine transport serves the flat ring only: its receive buffers are tied to one ring's arena)
+    intra, inter = Ring(topo.intra, tag="ring", transport="nccl"), Ring(topo.inter, tag="inter", transport="nccl")
     L, M, W, i = topo.L, topo.M, topo.W, topo.rank
     B, S, H = q.shape[0], q.shape[seq_dim], q.shape[3 - seq_dim]
     if mode == "zigzag":
@@ -289,22 +295,29 @@ def _ring_backward(d_o, q, k, v, out, lse, scale, seq_dim, mode, topo, determini
     f32 = dict(dtype=torch.float32, device=dev)
     dk_acc = torch.zeros(k.shape, **f32)
     dv_acc = torch.zeros(v.shape, **f32)
-    part = torch.zeros(q.shape, **f32)  # this round's dQ partial (the kernel reduce-adds into it)
 
     def round_kernel(r, j, bundle, dq_part):
         _bwd_dispatch(ops, mode, r, i, j, bundle, dq_part, k, v, dk_acc, dv_acc, scale, seq_dim, deterministic)
 
     bundle = [delta, d_o, q, lse.contiguous()]
+    # `part`: this round's dQ partial (the kernel reduce-adds into it)
     if W == 1:
+        part = torch.zeros(q.shape, **f32)
         round_kernel(1, i, bundle, part)
         dq_final = part
     elif topo.hier:
+        part = torch.zeros(q.shape, **f32)
         dq_final = _bwd_rounds_hier(ops, topo, round_kernel, bundle, part, q.shape, f32, seq_dim)
     else:
         ring = Ring(topo.group, tag="ring")
-        recv = [[torch.empty_like(t) for t in bundle] for _ in range(min(2, W - 1))]
+        # every buffer that is ever the destination of a hop comes from the ring (the copy-engine transport
+        # keeps them in its IPC-mapped arena): two bundle sets and the three rotating fp32 dQ buffers
+        ring.begin(q, [_nbytes(t) for t in bundle] * min(2, W - 1) + [4 * q.numel()] * 3)
+        recv = [[ring.empty_like(t) for t in bundle] for _ in range(min(2, W - 1))]
         hold = None                      # fp32 dQ accumulated for the bundle held in the previous round
-        spare = [torch.empty(q.shape, **f32), torch.empty(q.shape, **f32)]
+        part = ring.empty(q.shape, torch.float32, dev)
+        part.zero_()
+        spare = [ring.empty(q.shape, torch.float32, dev), ring.empty(q.shape, torch.float32, dev)]
         for r in range(1, W + 1):
             j = topo.source(r)
             srcs: List[torch.Tensor] = []
@@ -361,9 +374,9 @@ def _bwd_rounds_hier(ops, topo, round_kernel, bundle, part, qshape, f32, seq_dim
         L rounds of kernel time to hide behind.  After the last cycle the same step is the hop home.
     """
     L, M, W = topo.L, topo.M, topo.W
-    intra = Ring(topo.intra, tag="ring")
-    inter = Ring(topo.inter, tag="inter")
-    inter_q = Ring(topo.inter_dq if topo.inter_dq is not None else topo.inter, tag="inter_dq")
+    intra = Ring(topo.intra, tag="ring", transport="nccl")
+    inter = Ring(topo.inter, tag="inter", transport="nccl")
+    inter_q = Ring(topo.inter_dq if topo.inter_dq is not None else topo.inter, tag="inter_dq", transport="nccl")
     recv = [[torch.empty_like(t) for t in bundle] for _ in range(min(2, L - 1))]
     xbuf = [[torch.empty_like(t) for t in bundle] for _ in range(min(2, M - 1))]
     free: List[torch.Tensor] = []

@@ -10,6 +10,11 @@ awaited by ``wait``.  Two transports:
   sync (the reference's BMTrain side-stream variant, comm.py:267-283,313-317,
   is the model).  One communicator per (process group, tag), cached -- the
   reference builds a fresh ``Ring`` per call (burst_attn_interface.py:205,265,268).
+  With ``BA_RING_TRANSPORT=ce`` the flat ring instead pushes its hops with the copy
+  engines into a ring-owned, IPC-mapped receive arena (csrc/ring_ce.cu): zero SMs,
+  for shards short enough that NCCL's SM-resident kernels would be exposed.  Receive
+  buffers then come from ``Ring.empty_like`` (a bump allocator over the arena that
+  every rank drives identically, so offsets are symmetric).
 * ``torch`` (CPU tensors under gloo, used by the world_size-2 CPU tests of the
   ring schedule): ``dist.batch_isend_irecv`` as in comm.py:159-171,269.
 
@@ -25,6 +30,7 @@ W spanning several NVLink domains.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -54,14 +60,32 @@ def replicate(t: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------- #
 # native rings, cached per (process group, tag, device)
 # --------------------------------------------------------------------------- #
+class _DeviceBytes:
+    """A raw device allocation presented through the CUDA array interface (zero-copy ``torch.as_tensor``)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def _align(n: int, a: int = 1024) -> int:
+    return (n + a - 1) // a * a
+
+
 class _NativeRing:
-    def __init__(self, group, tag: str, device: torch.device):
+    def __init__(self, group, tag: str, device: torch.device, transport: str = "nccl"):
         self.lib = _n.lib()
+        self.group = group
+        self.device = device
         self.world = get_world_size(group)
         self.rank = get_rank(group)
+        self.ce = transport == "ce" and self.world > 1
+        self.arena: Optional[torch.Tensor] = None  # uint8 view of the receive arena (copy-engine transport)
+        self.arena_off = 0
         self.handle = ctypes.c_void_p()
         idbuf = (ctypes.c_uint8 * _n.NCCL_UNIQUE_ID_BYTES)()
-        if self.world > 1:
+        if self.ce:
+            idbuf = None  # no communicator: hops go through ba_ring_arena_* (csrc/ring_ce.cu)
+        elif self.world > 1:
             payload = [None]
             if self.rank == 0:
                 _n.check(self.lib.ba_ring_unique_id(idbuf), "ba_ring_unique_id")
@@ -87,15 +111,54 @@ class _NativeRing:
     def wait(self, device) -> None:
         _n.check(self.lib.ba_ring_wait(self.handle, _n.stream_ptr(device)), "ba_ring_wait")
 
+    # ---- receive arena of the copy-engine transport
+    def begin(self, nbytes: int) -> None:
+        """Start of one driver call that will carve ``nbytes`` of receive buffers.  Every rank passes the
+        same number (equal shards), so they all decide to grow in the same call."""
+        if not self.ce:
+            return
+        if self.arena is None or nbytes > self.arena.numel():
+            self._grow(nbytes + nbytes // 4)
+        self.arena_off = 0
 
-_native_rings: Dict[Tuple[int, str, int], _NativeRing] = {}
+    def _grow(self, nbytes: int) -> None:
+        # collective: nobody may still be pushing into (or reading from) the arena that is replaced
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        self.arena = None
+        base = ctypes.c_void_p()
+        hbuf = (ctypes.c_uint8 * _n.IPC_HANDLE_BYTES)()
+        with torch.cuda.device(self.device):
+            _n.check(self.lib.ba_ring_arena_create(self.handle, nbytes, ctypes.byref(base), hbuf),
+                     "ba_ring_arena_create")
+            handles: List[Optional[bytes]] = [None] * self.world
+            dist.all_gather_object(handles, bytes(hbuf), group=self.group)
+            prv = (ctypes.c_uint8 * _n.IPC_HANDLE_BYTES).from_buffer_copy(handles[(self.rank - 1) % self.world])
+            nxt = (ctypes.c_uint8 * _n.IPC_HANDLE_BYTES).from_buffer_copy(handles[(self.rank + 1) % self.world])
+            _n.check(self.lib.ba_ring_arena_connect(self.handle, prv, nxt), "ba_ring_arena_connect")
+        self.arena = torch.as_tensor(_DeviceBytes(base.value, _align(nbytes)), device=self.device)
+        dist.barrier(group=self.group)
+
+    def empty(self, shape, dtype) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= d
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        off = _align(self.arena_off)
+        assert self.arena is not None and off + nbytes <= self.arena.numel(), \
+            "receive arena exhausted: Ring.begin() was given too small a size"
+        self.arena_off = off + nbytes
+        return self.arena[off:off + nbytes].view(dtype).view(shape)
 
 
-def _native_ring(group, tag: str, device: torch.device) -> _NativeRing:
-    key = (id(group) if group is not None else 0, tag, device.index if device.index is not None else -1)
+_native_rings: Dict[Tuple[int, str, int, str], _NativeRing] = {}
+
+
+def _native_ring(group, tag: str, device: torch.device, transport: str = "nccl") -> _NativeRing:
+    key = (id(group) if group is not None else 0, tag, device.index if device.index is not None else -1, transport)
     ring = _native_rings.get(key)
     if ring is None:
-        ring = _NativeRing(group, tag, device)
+        ring = _NativeRing(group, tag, device, transport)
         _native_rings[key] = ring
     return ring
 
@@ -104,8 +167,11 @@ def _native_ring(group, tag: str, device: torch.device) -> _NativeRing:
 class Ring:
     """Single flat ring over ``process_group``: send to (rank+1)%W, receive from (rank-1)%W."""
 
-    def __init__(self, process_group=None, local_group=(None, None), dq: bool = False, tag: Optional[str] = None):
+    def __init__(self, process_group=None, local_group=(None, None), dq: bool = False, tag: Optional[str] = None,
+                 transport: Optional[str] = None):
         self.comm = process_group
+        self.transport = transport or os.environ.get("BA_RING_TRANSPORT", "nccl")
+        assert self.transport in ("nccl", "ce"), f"BA_RING_TRANSPORT must be nccl or ce, got {self.transport!r}"
         self.world_size = get_world_size(process_group)
         self.rank = get_rank(process_group)
         self.tag = tag or ("dq" if dq else "kv")
@@ -138,8 +204,7 @@ class Ring:
         self._pending = []
         if srcs[0].is_cuda:
             self._device = srcs[0].device
-            if self._native is None:
-                self._native = _native_ring(self.comm, self.tag, self._device)
+            self._ensure_native(self._device)
             self._native.post(srcs, dsts)
             self._reqs = ["native"]
         else:
@@ -174,3 +239,24 @@ class Ring:
     def post(self, srcs, dsts):
         self._ring_send_recv_base(srcs, dsts)
         self.commit()
+
+    def _ensure_native(self, device):
+        if self._native is None:
+            self._native = _native_ring(self.comm, self.tag, device, self.transport)
+
+    def begin(self, like: torch.Tensor, recv_sizes: Sequence[int]) -> None:
+        """Announce one driver call that will ask ``empty`` / ``empty_like`` for receive buffers of these byte
+        sizes (only the copy-engine transport cares: its buffers come from the ring's arena)."""
+        if like.is_cuda and self.world_size > 1 and self.transport == "ce":
+            self._device = like.device
+            self._ensure_native(like.device)
+            self._native.begin(sum(_align(n) for n in recv_sizes))
+
+    def empty(self, shape, dtype, device) -> torch.Tensor:
+        """A buffer that may be the DESTINATION of a hop on this ring."""
+        if self._native is not None and self._native.ce:
+            return self._native.empty(tuple(shape), dtype)
+        return torch.empty(tuple(shape), dtype=dtype, device=device)
+
+    def empty_like(self, t: torch.Tensor) -> torch.Tensor:
+        return self.empty(t.shape, t.dtype, t.device)

@@ -20,6 +20,7 @@ BA_DTYPE_FP16, BA_DTYPE_BF16 = 0, 1
 BA_MASK_NONE, BA_MASK_CAUSAL = 0, 1
 BA_FWD_FIRST, BA_FWD_LAST = 1, 2
 NCCL_UNIQUE_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 
 class NativeLibraryError(RuntimeError):
@@ -40,7 +41,8 @@ _lib = None
 _EXPORTS = (
     "ba_last_error", "ba_device_check", "ba_version", "ba_fwd_chunk", "ba_bwd_delta", "ba_bwd_chunk",
     "ba_cast_from_f32", "ba_accumulate_f32", "ba_ring_unique_id", "ba_ring_create", "ba_ring_post",
-    "ba_ring_wait", "ba_ring_rank", "ba_ring_world", "ba_ring_destroy", "ba_selftest",
+    "ba_ring_wait", "ba_ring_rank", "ba_ring_world", "ba_ring_destroy", "ba_ring_arena_create",
+    "ba_ring_arena_connect", "ba_selftest",
 )
 
 
@@ -89,6 +91,10 @@ def lib() -> ctypes.CDLL:
     L.ba_ring_world.argtypes = [vp]
     L.ba_ring_destroy.restype = i
     L.ba_ring_destroy.argtypes = [vp]
+    L.ba_ring_arena_create.restype = i
+    L.ba_ring_arena_create.argtypes = [vp, ctypes.c_int64, ctypes.POINTER(vp), vp]
+    L.ba_ring_arena_connect.restype = i
+    L.ba_ring_arena_connect.argtypes = [vp, vp, vp]
     L.ba_selftest.restype = i
     L.ba_selftest.argtypes = [i, vp, vp, vp, i, vp]
     _lib = L

@@ -5,18 +5,18 @@
 // NCCL is resolved at run time with dlopen so that the library shares the one
 // libnccl.so.2 the host process (PyTorch) already loaded instead of linking a
 // second copy.  One ring = one communicator + one high-priority stream + two
-// events; no host synchronisation anywhere.
+// events; no host synchronisation anywhere.  A ring whose receive arena has been connected
+// (ba_ring_arena_*, ring_ce.cu) posts its hops over the copy engines instead.
 #include <dlfcn.h>
 #include <string.h>
 
 #include <mutex>
 
-#include "host_common.h"
+#include "ring_internal.h"
 
 namespace ba {
 
 // Minimal NCCL ABI (stable since 2.7): opaque comm, 128-byte unique id, result enum.
-typedef struct ncclComm* ncclComm_t;
 typedef struct {
   char internal[BA_NCCL_UNIQUE_ID_BYTES];
 } ncclUniqueId;
@@ -72,13 +72,6 @@ static int nccl_fail(ncclResult_t r, const char* what) {
 
 }  // namespace ba
 
-struct ba_ring {
-  ba::ncclComm_t comm = nullptr;
-  int rank = 0, world = 1, device = 0;
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
-};
-
 extern "C" int ba_ring_unique_id(void* out_id128) {
   using namespace ba;
   BA_REQUIRE(out_id128, "ba_ring_unique_id: null output");
@@ -104,8 +97,7 @@ extern "C" int ba_ring_create(const void* id128, int rank, int world, ba_ring** 
   BA_CHECK_CUDA(cudaStreamCreateWithPriority(&r->side, cudaStreamNonBlocking, hi));
   BA_CHECK_CUDA(cudaEventCreateWithFlags(&r->ev_ready, cudaEventDisableTiming));
   BA_CHECK_CUDA(cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming));
-  if (world > 1) {
-    BA_REQUIRE(id128, "ba_ring_create: unique id required for world > 1");
+  if (world > 1 && id128) {  // id128 == NULL: a copy-engine-only ring (ba_ring_arena_*), no communicator
     if (!nccl().ok) {
       set_error("libnccl.so.2 could not be loaded");
       return BA_ERR_NCCL;
@@ -129,7 +121,11 @@ extern "C" int ba_ring_post(ba_ring* ring, const void* const* src, void* const* 
   if (ring->world == 1) {
     for (int i = 0; i < n; ++i)
       BA_CHECK_CUDA(cudaMemcpyAsync(dst[i], src[i], (size_t)nbytes[i], cudaMemcpyDeviceToDevice, ring->side));
+  } else if (ring->ce.connected) {
+    int rc = ce_post(ring, src, dst, nbytes, n);
+    if (rc != BA_OK) return rc;
   } else {
+    BA_REQUIRE(ring->comm, "ba_ring_post: the ring has neither a communicator nor a connected arena");
     const int next = (ring->rank + 1) % ring->world;
     const int prev = (ring->rank + ring->world - 1) % ring->world;
     BA_CHECK_NCCL(nccl().GroupStart());
@@ -157,6 +153,7 @@ extern "C" int ba_ring_destroy(ba_ring* ring) {
   using namespace ba;
   if (!ring) return BA_OK;
   if (ring->side) cudaStreamSynchronize(ring->side);
+  ce_destroy(ring);
   if (ring->comm && nccl().ok) nccl().CommDestroy(ring->comm);
   if (ring->ev_ready) cudaEventDestroy(ring->ev_ready);
   if (ring->ev_done) cudaEventDestroy(ring->ev_done);

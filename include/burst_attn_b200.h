@@ -115,6 +115,23 @@ int ba_ring_rank(const ba_ring* ring);
 int ba_ring_world(const ba_ring* ring);
 int ba_ring_destroy(ba_ring* ring);
 
+/* ---- copy-engine transport of a ring (optional; rings whose ranks share a node) ----
+ * NCCL's send/recv are SM-resident kernels that compete with the tile kernels; for short shards that
+ * exposes the hop.  A ring can instead own a RECEIVE ARENA: one device allocation per rank, carved
+ * identically on every rank (destination i of a post has the same offset everywhere), mapped into both
+ * neighbours with CUDA IPC.  Once connected, ba_ring_post pushes each source into the next rank's arena
+ * with peer cudaMemcpyAsync (copy engines over NVLink, zero SMs) and flow-controls with two hop counters
+ * per rank awaited by cuStreamWaitValue32 -- same post/wait contract, still no host synchronisation.
+ *   ba_ring_arena_create : (re)allocates the local arena of `bytes` data bytes; returns its data base and
+ *                          a 64-byte IPC handle to hand to both neighbours (any host channel).  All ranks
+ *                          must be quiescent (device-synchronised + barrier) when an arena is replaced.
+ *   ba_ring_arena_connect: maps the previous and the next rank's arenas.  From here on every destination
+ *                          passed to ba_ring_post must lie inside the local arena.
+ * A ring created with id128 == NULL has no NCCL communicator and must be connected before its first post. */
+#define BA_IPC_HANDLE_BYTES 64
+int ba_ring_arena_create(ba_ring* ring, int64_t bytes, void** base_out, void* handle_out64);
+int ba_ring_arena_connect(ba_ring* ring, const void* prev_handle64, const void* next_handle64);
+
 /* ---- self tests of the sm_100a building blocks (tests/ only) --------------------
  * mode 0: S[128,128] fp32 = A[128,128] * B[128,128]^T through TMA + tcgen05 SS MMA
  * mode 1: O[128,128] fp32 = P[128,128] * V[128,128] with P staged in TMEM (TS MMA)

@@ -45,6 +45,10 @@ def test_bad_arguments_return_error_string(nat):
     assert rc != 0 and b"null" in L.ba_last_error()
     rc = L.ba_ring_post(None, None, None, None, 0, None)
     assert rc != 0
+    rc = L.ba_ring_arena_create(None, 1 << 20, None, None)
+    assert rc != 0 and b"ba_ring_arena_create" in L.ba_last_error()
+    rc = L.ba_ring_arena_connect(None, None, None)
+    assert rc != 0 and b"ba_ring_arena_connect" in L.ba_last_error()
     assert L.ba_version() >= 100
 
 
@@ -53,3 +57,25 @@ def test_missing_library_fails_loudly(nat, monkeypatch):
     monkeypatch.setattr(nat, "LIB_PATH", "/nonexistent/libburst_attn_b200.so")
     with pytest.raises(nat.NativeLibraryError):
         nat.lib()
+
+
+def test_receive_arena_bump_allocator_is_symmetric_and_aligned():
+    """Host logic of the copy-engine transport's receive arena (burst_attn/comm.py): buffers are carved in
+    call order at 1 KiB-aligned offsets, so equal call sequences give equal offsets on every rank, and the
+    size announced by Ring.begin covers them."""
+    import torch
+    from burst_attn import comm
+
+    ring = comm._NativeRing.__new__(comm._NativeRing)  # no library / device needed for the carving logic
+    ring.ce = True
+    sizes = [3 * 5 * 7 * 2, 1024, 4 * 33]
+    ring.arena = torch.zeros(sum(comm._align(n) for n in sizes), dtype=torch.uint8)
+    ring.arena_off = 0
+    a = ring.empty((3, 5, 7), torch.bfloat16)
+    b = ring.empty((256,), torch.float32)
+    c = ring.empty((33,), torch.float32)
+    base = ring.arena.data_ptr()
+    assert [t.data_ptr() - base for t in (a, b, c)] == [0, 1024, 2048]
+    assert a.shape == (3, 5, 7) and a.dtype == torch.bfloat16 and c.is_contiguous()
+    with pytest.raises(AssertionError):
+        ring.empty((1,), torch.float32)  # beyond what begin() announced

@@ -31,5 +31,20 @@ else
       > gpurun_out/bench_n${N}_double$dr.json 2> gpurun_out/bench_n${N}_double$dr.err
     tail -1 gpurun_out/bench_n${N}_double$dr.json
   done
+  # 5. copy-engine transport (never run before): parity at N ranks under a SHORT timeout, then the short-shard
+  #    bench point where NCCL's hop is exposed (S_local = 65536/N), both transports
+  BA_RING_TRANSPORT=ce timeout 180 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N \
+    --master-addr 127.0.0.1 --master-port 29543 tests/ring_check.py > gpurun_out/ring_check_ce_n$N.txt 2>&1
+  tail -8 gpurun_out/ring_check_ce_n$N.txt
+  if grep -q FAIL gpurun_out/ring_check_ce_n$N.txt || ! grep -q PASS gpurun_out/ring_check_ce_n$N.txt; then
+    echo "copy-engine ring not healthy: skipping its bench"
+  else
+    for tr in nccl ce; do
+      BA_RING_TRANSPORT=$tr timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$N \
+        --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus $N --seq 65536 --steps 5 --warmup 3 --no-e2e \
+        > gpurun_out/bench_n${N}_s65536_$tr.json 2> gpurun_out/bench_n${N}_s65536_$tr.err
+      tail -1 gpurun_out/bench_n${N}_s65536_$tr.json
+    done
+  fi
 fi
 ls -la gpurun_out
