@@ -42,7 +42,7 @@ _EXPORTS = (
     "ba_last_error", "ba_device_check", "ba_version", "ba_fwd_chunk", "ba_bwd_delta", "ba_bwd_chunk",
     "ba_cast_from_f32", "ba_accumulate_f32", "ba_ring_unique_id", "ba_ring_create", "ba_ring_post",
     "ba_ring_wait", "ba_ring_rank", "ba_ring_world", "ba_ring_destroy", "ba_ring_arena_create",
-    "ba_ring_arena_connect", "ba_selftest",
+    "ba_ring_arena_connect", "ba_selftest", "ba_ubench",
 )
 
 
@@ -95,6 +95,8 @@ def lib() -> ctypes.CDLL:
     L.ba_ring_arena_create.argtypes = [vp, ctypes.c_int64, ctypes.POINTER(vp), vp]
     L.ba_ring_arena_connect.restype = i
     L.ba_ring_arena_connect.argtypes = [vp, vp, vp]
+    L.ba_ubench.restype = i
+    L.ba_ubench.argtypes = [i, i, i, ctypes.POINTER(ctypes.c_int64), vp]
     L.ba_selftest.restype = i
     L.ba_selftest.argtypes = [i, vp, vp, vp, i, vp]
     _lib = L

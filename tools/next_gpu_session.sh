@@ -6,6 +6,13 @@
 set -x
 mkdir -p gpurun_out
 if [ "$1" != "multi" ]; then
+  # 0. building-block rates the next kernel designs hinge on: seconds of GPU time
+  for part in single pair; do
+    for grid in 1 148; do
+      timeout 120 python tools/ubench.py --part $part --grid $grid >> gpurun_out/ubench.txt 2>&1
+    done
+  done
+  cat gpurun_out/ubench.txt
   # 1. full parity suite incl. the head_dim-64 (C1) tests that have not run on a GPU yet
   timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.txt 2>&1; tail -3 gpurun_out/pytest_gpu.txt
   # 2. the CTA-pair forward variants under the forward + API tests (gate for switching the default)
