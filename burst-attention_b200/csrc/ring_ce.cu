@@ -88,12 +88,17 @@ int ce_post(ba_ring* r, const void* const* src, void* const* dst, const int64_t*
   return BA_OK;
 }
 
-static void ce_release(ba_ring* r) {
+// Unmap the neighbours' arenas and RETIRE (not free) the local one: a neighbour may still have it mapped, and
+// freeing exported memory before every importer has closed it is undefined.  The retired arena is freed in
+// ba_ring_arena_connect, which the host calls only after a collective that every rank enters after its own
+// ba_ring_arena_create -- i.e. after every importer has closed its mapping.
+static void ce_disconnect(ba_ring* r) {
   CeState& ce = r->ce;
   if (r->side) cudaStreamSynchronize(r->side);
   if (ce.next_map) cudaIpcCloseMemHandle(ce.next_map);
   if (ce.prev_map && ce.prev_map != ce.next_map) cudaIpcCloseMemHandle(ce.prev_map);
-  if (ce.base) cudaFree(ce.base);
+  if (ce.retired) cudaFree(ce.retired);  // two growths ago: long unmapped everywhere
+  ce.retired = ce.base;
   ce.base = ce.next_map = ce.prev_map = nullptr;
   ce.bytes = 0;
   ce.hop = 0;
@@ -101,7 +106,9 @@ static void ce_release(ba_ring* r) {
 }
 
 void ce_destroy(ba_ring* r) {
-  ce_release(r);
+  ce_disconnect(r);
+  if (r->ce.retired) cudaFree(r->ce.retired);
+  r->ce.retired = nullptr;
   if (r->ce.host_vals) cudaFreeHost(r->ce.host_vals);
   r->ce.host_vals = nullptr;
 }
@@ -117,7 +124,7 @@ extern "C" int ba_ring_arena_create(ba_ring* ring, int64_t bytes, void** base_ou
     set_error("cuStreamWaitValue32 / cuStreamWriteValue32 driver entry points not available");
     return BA_ERR_UNSUPPORTED;
   }
-  ce_release(ring);  // the caller has quiesced every rank (see burst_attn/comm.py)
+  ce_disconnect(ring);  // the caller has quiesced every rank (see burst_attn/comm.py)
   CeState& ce = ring->ce;
   bytes = (bytes + 1023) / 1024 * 1024;
   BA_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(&ce.base), (size_t)(bytes + kCeHeader)));
@@ -147,6 +154,10 @@ extern "C" int ba_ring_arena_connect(ba_ring* ring, const void* prev_handle64, c
     ce.prev_map = ce.next_map;  // world == 2: one neighbour, one mapping
   } else {
     BA_CHECK_CUDA(cudaIpcOpenMemHandle(reinterpret_cast<void**>(&ce.prev_map), hp, cudaIpcMemLazyEnablePeerAccess));
+  }
+  if (ce.retired) {  // every rank has been through its ba_ring_arena_create: nobody maps the old arena any more
+    BA_CHECK_CUDA(cudaFree(ce.retired));
+    ce.retired = nullptr;
   }
   ce.hop = 0;
   ce.connected = true;

@@ -9,6 +9,7 @@ typedef struct ncclComm* ncclComm_t;
 // neighbours with CUDA IPC; flags live in the arena's first page.
 struct CeState {
   uint8_t* base = nullptr;      // local arena (cudaMalloc): [0, kCeHeader) flags, then data
+  uint8_t* retired = nullptr;   // previous arena, kept until no neighbour can still have it mapped
   int64_t bytes = 0;            // data bytes (without the header)
   uint8_t* next_map = nullptr;  // next rank's arena in this process' address space
   uint8_t* prev_map = nullptr;  // previous rank's arena (== next_map when world == 2)

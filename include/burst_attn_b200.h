@@ -125,7 +125,8 @@ int ba_ring_destroy(ba_ring* ring);
  *   ba_ring_arena_create : (re)allocates the local arena of `bytes` data bytes; returns its data base and
  *                          a 64-byte IPC handle to hand to both neighbours (any host channel).  All ranks
  *                          must be quiescent (device-synchronised + barrier) when an arena is replaced.
- *   ba_ring_arena_connect: maps the previous and the next rank's arenas.  From here on every destination
+ *   ba_ring_arena_connect: maps the previous and the next rank's arenas (and frees a replaced arena).  Call it
+ *                          only after a collective that follows every rank's ba_ring_arena_create.  From here on every destination
  *                          passed to ba_ring_post must lie inside the local arena.
  * A ring created with id128 == NULL has no NCCL communicator and must be connected before its first post. */
 #define BA_IPC_HANDLE_BYTES 64
