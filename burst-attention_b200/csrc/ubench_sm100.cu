@@ -26,7 +26,7 @@ BA_DEVICE long long clk() {
 }
 
 // ---- single-CTA modes
-// 0 SS N=128 | 1 TS N=128 | 2 SS N=256 | 3 TS N=256 | 4 SS N=64 | 8 LDTM 4 warps | 9 LDTM 8 warps
+// 0 SS N=128 | 1 TS N=128 | 2 SS N=256 | 3 TS N=256 | 4 SS N=64 | 8 LDTM 4 warps | 9 LDTM 8 warps | 16 LDTM 1 warp
 // 10 STTM 4 warps | 11 MUFU ex2, 8 warps | 12 one MMA + commit + wait (latency) | 14 TS N=128 chain with 4 warps
 // of LDTM running beside it (out[0] = MMA cycles, out[1] = LDTM cycles for the same number of groups)
 __global__ void __launch_bounds__(kUbThreads, 1) ubench_kernel(int mode, int iters, long long* out) {
@@ -77,8 +77,8 @@ __global__ void __launch_bounds__(kUbThreads, 1) ubench_kernel(int mode, int ite
     cyc = clk() - t0;
     if (lane == 0) atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)cyc);
   }
-  const int ld_warps = (mode == 9) ? 8 : 4;
-  if (warp < ld_warps && (mode == 8 || mode == 9 || mode == 14)) {
+  const int ld_warps = (mode == 9) ? 8 : (mode == 16 ? 1 : 4);
+  if (warp < ld_warps && (mode == 8 || mode == 9 || mode == 14 || mode == 16)) {
     uint32_t v[32], x = 0;
     const uint32_t col0 = tb + lane_base + 384;  // columns no MMA of this benchmark touches
     const long long t0 = clk();
@@ -217,10 +217,11 @@ __global__ void __launch_bounds__(kUbThreads, 1) ubench2_kernel(int mode, int it
 
 extern "C" int ba_ubench(int mode, int iters, int grid, int64_t* out4_host, void* stream) {
   using namespace ba;
-  BA_REQUIRE(mode >= 0 && mode <= 15 && iters > 0 && iters <= (1 << 20) && grid >= 1 && out4_host,
+  BA_REQUIRE(mode >= 0 && mode <= 16 && iters > 0 && iters <= (1 << 20) && grid >= 1 && out4_host,
              "ba_ubench: bad arguments (mode %d, iters %d, grid %d)", mode, iters, grid);
   const bool pair = (mode >= 5 && mode <= 7) || mode == 13 || mode == 15;
-  BA_REQUIRE(pair || mode <= 4 || (mode >= 8 && mode <= 12) || mode == 14, "ba_ubench: unknown mode %d", mode);
+  BA_REQUIRE(pair || mode <= 4 || (mode >= 8 && mode <= 12) || mode == 14 || mode == 16, "ba_ubench: unknown mode %d",
+             mode);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   long long* d = nullptr;
   BA_CHECK_CUDA(cudaMalloc(reinterpret_cast<void**>(&d), 4 * sizeof(long long)));

@@ -145,7 +145,7 @@ int ba_selftest(int mode, const void* a, const void* b, void* out, int dtype, vo
 /* ---- micro-benchmarks of the sm_100a building blocks (tools/ubench.py only) -------------------
  * Runs one timing kernel (`grid` CTAs, or CTA pairs for the cta_group::2 modes) and returns device clock
  * cycles in out4_host[0] (and [1] for mode 14); synchronises the stream.  Modes: 0-4 tcgen05.mma chains of
- * `iters` dispatches (SS/TS, N = 128/256/64), 5-7 the same on CTA pairs (M = 256), 8-10 tcgen05.ld / st
+ * `iters` dispatches (SS/TS, N = 128/256/64), 5-7 the same on CTA pairs (M = 256), 8-10 and 16 tcgen05.ld / st
  * groups, 11 MUFU ex2, 12 single-MMA latency, 13 / 15 cluster-remote arrive and multicast-commit round
  * trips, 14 a TS chain with tcgen05.ld traffic beside it (csrc/ubench_sm100.cu).                       */
 int ba_ubench(int mode, int iters, int grid, int64_t* out4_host, void* stream);

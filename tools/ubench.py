@@ -57,7 +57,8 @@ def main():
             c = run(lib, mode, 64, 2)[0]
             print(f"{label:44s} {c / 64:8.1f} clk")
         return
-    for mode, label, nw in ((8, "tcgen05.ld x32, 4 warps", 4), (9, "tcgen05.ld x32, 8 warps", 8),
+    for mode, label, nw in ((16, "tcgen05.ld x32, 1 warp", 1), (8, "tcgen05.ld x32, 4 warps", 4),
+                            (9, "tcgen05.ld x32, 8 warps", 8),
                             (10, "tcgen05.st x32, 4 warps", 4)):
         c = run(lib, mode, a.iters, a.grid)[0]
         nbytes = a.iters * 4 * 32 * 4 * 32 * nw  # groups x 4 instr x 32 cols x 4 B x 32 lanes x warps
