@@ -122,9 +122,10 @@ def test_ring_driver_matches_dense(world, case):
 @pytest.mark.parametrize("world,intra,case,dq_groups", [
     (4, 2, "none", False), (4, 2, "zigzag", True), (4, 2, "striped", False),
     (6, 3, "zigzag", False), (6, 2, "none", True), (6, 2, "striped", False),
+    (8, 4, "striped", True), (8, 2, "zigzag", False),
 ])
 def test_double_ring_matches_dense(world, intra, case, dq_groups):
-    """Hierarchical (double) ring, W = L*M with (L, M) in {(2,2), (3,2), (2,3)}: K/V and Q-bundle prefetch
+    """Hierarchical (double) ring, W = L*M with (L, M) in {(2,2), (3,2), (2,3), (4,2), (2,4)}: K/V and Q-bundle prefetch
     across nodes, dQ node sums chained along the inter-node ring (reference test_burst.py:239-247
     ``double_ring`` axis)."""
     ctx = mp.get_context("spawn")
@@ -243,6 +244,42 @@ def test_l2_blocking_of_rounds_matches_dense(monkeypatch, blk):
             for a, b in zip(g, (dq, dk, dv)):
                 torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5)
             assert sum(1 for c in ops.calls if c[0] == "fwd") > 1 and sum(1 for c in ops.calls if c[0] == "bwd") > 1
+    finally:
+        chunk_ops._set_ops_for_testing(None)
+
+
+def test_l2_blocking_random_shapes(monkeypatch):
+    """Seeded sweep over (S, block size, batch, heads, causal flavour): the offset / view arithmetic of the
+    L2-blocked rounds (row starts rounded to tile pairs, causal offsets of sub-views, ragged tails) against
+    dense attention, forward and backward."""
+    import random
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from burst_attn import burst_attn_func, burst_attn_func_striped, chunk_ops
+    from oracle import attention_oracle as orc
+    from oracle_ops import OracleOps
+    ops = OracleOps()
+    chunk_ops._set_ops_for_testing(ops)
+    rng = random.Random(20240917)
+    try:
+        for case in range(24):
+            S = rng.choice([17, 64, 100, 255, 256, 257, 300, 513, 640])
+            blk = rng.choice([8, 16, 24, 100, 128, 256])
+            Bn, Hn = rng.choice([1, 2]), rng.choice([1, 3])
+            func, causal = rng.choice([(burst_attn_func, False), (burst_attn_func, True),
+                                       (burst_attn_func_striped, True)])
+            if causal and func is burst_attn_func and S % 2:
+                S += 1  # zigzag halves
+            monkeypatch.setenv("BA_L2_BLOCK", str(blk))
+            torch.manual_seed(case)
+            q, k, v, do = (torch.randn(Bn, S, Hn, 8, dtype=torch.float64) for _ in range(4))
+            qq, kk, vv = (t.clone().requires_grad_() for t in (q, k, v))
+            o = func(qq, kk, vv, None, "cuda", causal)
+            g = torch.autograd.grad(o, (qq, kk, vv), do)
+            o_ref, _, dq, dk, dv = orc.dense_attention_bwd(q, k, v, do, None, causal)
+            msg = f"case {case}: S={S} blk={blk} B={Bn} H={Hn} {func.__name__} causal={causal}"
+            torch.testing.assert_close(o.detach(), o_ref, rtol=1e-5, atol=1e-5, msg=lambda m: f"{msg}: {m}")
+            for a, b in zip(g, (dq, dk, dv)):
+                torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5, msg=lambda m: f"{msg}: {m}")
     finally:
         chunk_ops._set_ops_for_testing(None)
 
