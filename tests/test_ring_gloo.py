@@ -24,6 +24,37 @@ def _free_port():
     return p
 
 
+def _install_deferred_transport():
+    """Make the CPU transport behave like the asynchronous GPU one, to catch buffer hazards gloo's eager
+    transfers hide: between ``post`` and ``wait`` a hop's destinations hold garbage (poisoned with NaN here, so
+    any read before ``wait`` shows up in the results) and its sources must not change (snapshotted at ``post``
+    and compared at ``wait``, which is when the transfer actually runs)."""
+    from burst_attn import comm
+
+    eager_commit = comm.Ring._commit_torch
+
+    def commit(self, srcs, dsts):
+        assert not getattr(self, "_deferred", None), "two hops in flight on one ring"
+        self._deferred = (srcs, dsts, [s.clone() for s in srcs])
+        for d in dsts:
+            d.fill_(float("nan"))
+        return ["deferred"]
+
+    def wait(self, force_wait_inter=False):
+        for r in self._reqs:
+            assert r == "deferred"
+            srcs, dsts, snap = self._deferred
+            self._deferred = None
+            for s, c in zip(srcs, snap):
+                assert torch.equal(s, c), "a hop's source was modified between post and wait"
+            for q in eager_commit(self, srcs, dsts):
+                q.wait()
+        self._reqs = []
+
+    comm.Ring._commit_torch = commit
+    comm.Ring.wait = wait
+
+
 def _worker(rank, world, port, case, seq_dim, errq, intra=0, dq_groups=False):
     try:
         for p in (ROOT, os.path.join(ROOT, "burst-attention_b200"), os.path.join(ROOT, "tests")):
@@ -37,6 +68,8 @@ def _worker(rank, world, port, case, seq_dim, errq, intra=0, dq_groups=False):
         from oracle_ops import OracleOps
         ops = OracleOps()
         chunk_ops._set_ops_for_testing(ops)
+        if os.environ.get("BA_TEST_DEFERRED"):
+            _install_deferred_transport()
 
         func, causal, layout = {
             "none": (burst_attn_func, False, "contiguous"),
@@ -132,6 +165,27 @@ def test_double_ring_matches_dense(world, intra, case, dq_groups):
     errq = ctx.SimpleQueue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, case, 1, errq, intra, dq_groups)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+    errs = []
+    while not errq.empty():
+        errs.append(errq.get())
+    assert not errs, "\n".join(errs)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+
+
+@pytest.mark.parametrize("world,intra,case", [(4, 0, "none"), (4, 0, "zigzag"), (4, 0, "striped"),
+                                              (4, 2, "zigzag"), (6, 2, "striped"), (6, 3, "none")])
+def test_no_buffer_hazards_with_asynchronous_transport(world, intra, case, monkeypatch):
+    """Flat and hierarchical rings under a transport that only moves data at ``wait`` and poisons the
+    destinations at ``post`` (see _install_deferred_transport): what the side-stream transport does on GPUs."""
+    monkeypatch.setenv("BA_TEST_DEFERRED", "1")
+    ctx = mp.get_context("spawn")
+    errq = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, 1, errq, intra, False)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
