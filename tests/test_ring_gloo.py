@@ -32,9 +32,20 @@ def _install_deferred_transport():
     from burst_attn import comm
 
     eager_commit = comm.Ring._commit_torch
+    plain_empty = comm.Ring.empty
+
+    def empty(self, shape, dtype, device):
+        t = plain_empty(self, shape, dtype, device)
+        self.__dict__.setdefault("_owned", set()).add(t.data_ptr())
+        return t
+
+    comm.Ring.empty = empty
 
     def commit(self, srcs, dsts):
         assert not getattr(self, "_deferred", None), "two hops in flight on one ring"
+        if self.transport == "ce":  # copy-engine rings can only receive into buffers carved from their arena
+            assert all(d.data_ptr() in getattr(self, "_owned", ()) for d in dsts), \
+                "a hop destination was not allocated through Ring.empty / empty_like"
         self._deferred = (srcs, dsts, [s.clone() for s in srcs])
         for d in dsts:
             d.fill_(float("nan"))
@@ -182,6 +193,7 @@ def test_no_buffer_hazards_with_asynchronous_transport(world, intra, case, monke
     """Flat and hierarchical rings under a transport that only moves data at ``wait`` and poisons the
     destinations at ``post`` (see _install_deferred_transport): what the side-stream transport does on GPUs."""
     monkeypatch.setenv("BA_TEST_DEFERRED", "1")
+    monkeypatch.setenv("BA_RING_TRANSPORT", "ce")  # CPU tensors still travel over gloo; turns on the arena check
     ctx = mp.get_context("spawn")
     errq = ctx.SimpleQueue()
     port = _free_port()
