@@ -117,12 +117,19 @@ selftest_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 //         [128r,128r+128) and B rows [64r,64r+64), i.e. half of N)
 // mode 5: out[256,128] = A[256,128] * B[128,128]     (TS, A staged in each CTA's TMEM; B = [k][n] read
 //         MN-major, CTA r holds n columns [64r, 64r+64))
+// mode 6: probe of the M = 128 cta_group::2 accumulator layout (needed by the pair backward's dQ): a is
+//         [128,128]; CTA r holds A rows [64r,64r+64) and B rows [64r,64r+64); every TMEM cell of columns
+//         [0,128) is first set to the sentinel 12345.0, then out[r][lane][col] = raw dump of CTA r's TMEM.
+// mode 7: mode 4 (M = 256 SS) with the B halves delivered by the PEER's threads through DSMEM stores
+//         (st.shared::cluster + fence.proxy.async + cluster barrier) instead of TMA: the hand-off the pair
+//         backward uses for dS.
 constexpr int kSt2Smem = kStTile + kStBox + 1024 + 64;
 
 template <bool kBF16>
 __global__ void __launch_bounds__(128, 1)
 selftest2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
-                 const uint16_t* __restrict__ a_raw, float* __restrict__ out, int mode) {
+                 const uint16_t* __restrict__ a_raw, const uint16_t* __restrict__ b_raw, float* __restrict__ out,
+                 int mode) {
   extern __shared__ __align__(1024) uint8_t smem_raw2[];
   uint8_t* smem = smem_raw2;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -151,13 +158,19 @@ selftest2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
 
   if (t == 0) {
-    const uint32_t bytes_per_cta = (mode == 4 ? kStTile : 0) + kStBox;
+    const uint32_t bytes_per_cta = mode == 4 ? kStTile + kStBox : (mode == 7 ? kStTile : (mode == 6 ? 2 * kStBox : kStBox));
     if (rank == 0) mbar_arrive_expect_tx(bar_load, 2 * bytes_per_cta);
-    if (mode == 4) {
+    if (mode == 4 || mode == 7) {
       for (int half = 0; half < 2; ++half)
         tma_load_4d_2cta(sA + half * kStBox, &tmA, bar_load, half * 64, 0, (int)rank * 128, 0);
-      for (int half = 0; half < 2; ++half)  // B rows [64r, 64r+64): two 64x64 boxes of 8 KiB
+      if (mode == 4)
+        for (int half = 0; half < 2; ++half)  // B rows [64r, 64r+64): two 64x64 boxes of 8 KiB
+          tma_load_4d_2cta(sB + half * (kStBox / 2), &tmBh, bar_load, half * 64, 0, (int)rank * 64, 0);
+    } else if (mode == 6) {
+      for (int half = 0; half < 2; ++half) {  // A rows and B rows [64r, 64r+64): 64x64 boxes
+        tma_load_4d_2cta(sA + half * (kStBox / 2), &tmA, bar_load, half * 64, 0, (int)rank * 64, 0);
         tma_load_4d_2cta(sB + half * (kStBox / 2), &tmBh, bar_load, half * 64, 0, (int)rank * 64, 0);
+      }
     } else {
       // B[k][n]: this CTA's n columns [64r, 64r+64), all 128 k rows: one 128x64 box of 16 KiB
       tma_load_4d_2cta(sB, &tmBh, bar_load, (int)rank * 64, 0, 0, 0);
@@ -173,14 +186,33 @@ selftest2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tmem_st_x32(tmem_base + lane_base + 128 + 32, v + 32);
     tmem_wait_st();
   }
+  if (mode == 6) {  // sentinel in every cell the MMA could own
+    uint32_t v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(12345.0f);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_st_x32(tmem_base + lane_base + c * 32, v);
+    tmem_wait_st();
+  }
+  if (mode == 7) {
+    // thread t writes row (t % 64), 64-column box (t / 64) of the PEER's B half into the peer's sB, in the
+    // SWIZZLE_128B K-major layout a TMA box load would have produced (16-byte chunk j of row r at j ^ (r % 8))
+    const uint32_t peer = rank ^ 1u;
+    const int row = t & 63, box = t >> 6;
+    const uint4* src = reinterpret_cast<const uint4*>(b_raw + ((int)peer * 64 + row) * 128 + box * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      st_shared_remote_v4(sB + box * (kStBox / 2) + row * 128 + ((j ^ (row & 7)) << 4), peer, src[j]);
+    fence_proxy_async_all();
+  }
   tc_fence_before();
-  cluster_sync_all();  // A rows of BOTH CTAs are in TMEM before the leader issues
+  cluster_sync_all();  // A rows of BOTH CTAs are in TMEM (mode 5) / the DSMEM writes have landed (mode 7)
   tc_fence_after();
 
   if (rank == 0 && warp == 0) {
     mbar_wait(bar_load, 0);
     tc_fence_after();
-    if (mode == 4) {
+    if (mode == 4 || mode == 7) {
       constexpr uint32_t idesc = make_idesc(kBF16, 256, 128, false, false);
       const uint64_t a0 = make_smem_desc(smem_u32(sA), 16, 1024);
       const uint64_t b0 = make_smem_desc(smem_u32(sB), 16, 1024);
@@ -188,6 +220,14 @@ selftest2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t offA = (kk >> 2) * kStBox + (kk & 3) * 32;
         const uint32_t offB = (kk >> 2) * (kStBox / 2) + (kk & 3) * 32;
         umma_ss_2cta(tmem_base, desc_advance(a0, offA), desc_advance(b0, offB), idesc, kk > 0);
+      }
+    } else if (mode == 6) {
+      constexpr uint32_t idesc = make_idesc(kBF16, 128, 128, false, false);  // M = 128 over the pair: 64 rows per CTA
+      const uint64_t a0 = make_smem_desc(smem_u32(sA), 16, 1024);
+      const uint64_t b0 = make_smem_desc(smem_u32(sB), 16, 1024);
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint32_t off = (kk >> 2) * (kStBox / 2) + (kk & 3) * 32;
+        umma_ss_2cta(tmem_base, desc_advance(a0, off), desc_advance(b0, off), idesc, kk > 0);
       }
     } else {
       constexpr uint32_t idesc = make_idesc(kBF16, 256, 128, false, true);
@@ -217,16 +257,18 @@ selftest2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 extern "C" int ba_selftest(int mode, const void* a, const void* b, void* out, int dtype, void* stream) {
   using namespace ba;
-  BA_REQUIRE(mode >= 0 && mode <= 5, "ba_selftest: bad mode %d", mode);
+  BA_REQUIRE(mode >= 0 && mode <= 7, "ba_selftest: bad mode %d", mode);
   BA_REQUIRE(a && b && out, "ba_selftest: null pointer");
-  if (mode >= 4) {  // CTA-pair tests: a is [256,128], b [128,128], out fp32 [256,128]
-    ba_tensor4 ta{const_cast<void*>(a), 256 * 128, 128, 128};
+  if (mode >= 4) {  // CTA-pair tests: a is [256,128] ([128,128] in mode 6), b [128,128], out fp32 [256,128]
+    const int a_rows = mode == 6 ? 128 : 256;
+    ba_tensor4 ta{const_cast<void*>(a), (int64_t)a_rows * 128, 128, 128};
     ba_tensor4 tb{const_cast<void*>(b), 128 * 128, 128, 128};
     CUtensorMap tmA, tmBh;
     int rc;
-    if ((rc = make_tensor_map(&tmA, ta, 1, 256, 1, 128, lowp_dtype(dtype), 2, 64, 128, true))) return rc;
-    // mode 4: boxes of 64 rows x 64 cols (half of N); mode 5: 128 rows (k) x 64 cols (half of n)
-    if ((rc = make_tensor_map(&tmBh, tb, 1, 128, 1, 128, lowp_dtype(dtype), 2, 64, mode == 4 ? 64 : 128, true)))
+    if ((rc = make_tensor_map(&tmA, ta, 1, a_rows, 1, 128, lowp_dtype(dtype), 2, 64, mode == 6 ? 64 : 128, true)))
+      return rc;
+    // modes 4, 6, 7: boxes of 64 rows x 64 cols (half of N); mode 5: 128 rows (k) x 64 cols (half of n)
+    if ((rc = make_tensor_map(&tmBh, tb, 1, 128, 1, 128, lowp_dtype(dtype), 2, 64, mode == 5 ? 128 : 64, true)))
       return rc;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2);
@@ -241,13 +283,14 @@ extern "C" int ba_selftest(int mode, const void* a, const void* b, void* out, in
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const uint16_t* a16 = static_cast<const uint16_t*>(a);
+    const uint16_t* b16 = static_cast<const uint16_t*>(b);
     float* o32 = static_cast<float*>(out);
     if (dtype == BA_DTYPE_BF16) {
       BA_CHECK_CUDA(cudaFuncSetAttribute(selftest2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSt2Smem));
-      BA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, selftest2_kernel<true>, tmA, tmBh, a16, o32, mode));
+      BA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, selftest2_kernel<true>, tmA, tmBh, a16, b16, o32, mode));
     } else {
       BA_CHECK_CUDA(cudaFuncSetAttribute(selftest2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSt2Smem));
-      BA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, selftest2_kernel<false>, tmA, tmBh, a16, o32, mode));
+      BA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, selftest2_kernel<false>, tmA, tmBh, a16, b16, o32, mode));
     }
     return BA_OK;
   }

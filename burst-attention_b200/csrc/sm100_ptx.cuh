@@ -374,6 +374,18 @@ BA_DEVICE void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
       : "r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
+// 16-byte store into the shared memory of CTA `cta` of the cluster at the same offset as local `p` (DSMEM)
+BA_DEVICE void st_shared_remote_v4(void* p, uint32_t cta, uint4 v) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.v4.b32 [ra], {%2, %3, %4, %5};\n\t}\n"
+      :
+      : "r"(smem_u32(p)), "r"(cta), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+      : "memory");
+}
+// generic-proxy writes (any state space, incl. remote shared memory) -> visible to the async proxy (TMA, tcgen05)
+BA_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // lean (lo, hi) forms of the pair MMAs
 BA_DEVICE void umma_ts_2cta_lh(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                uint32_t accumulate) {

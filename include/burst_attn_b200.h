@@ -139,7 +139,10 @@ int ba_ring_arena_connect(ba_ring* ring, const void* prev_handle64, const void* 
  * mode 2: raw dump of a TMA-loaded 128x64 SWIZZLE_128B box (16 KiB)
  * mode 3: out = A^T * B with both operands MN-major (backward's dQ path)
  * a, b: dtype [128,128] row-major; out: fp32 [128,128] (mode 2: 8192 x 16-bit).
- * mode 4/5: CTA-pair (cta_group::2, cluster of 2) SS / TS GEMM: a [256,128], b [128,128], out fp32 [256,128]. */
+ * mode 4/5: CTA-pair (cta_group::2, cluster of 2) SS / TS GEMM: a [256,128], b [128,128], out fp32 [256,128].
+ * mode 6: TMEM layout probe of an M = 128 cta_group::2 MMA (a [128,128]; out = raw [2][128 lanes][128 cols] dump,
+ *         12345.0 where nothing was written); mode 7: mode 4 with the B halves delivered through DSMEM stores
+ *         by the peer CTA (tools/probe_pair.py).                                                              */
 int ba_selftest(int mode, const void* a, const void* b, void* out, int dtype, void* stream);
 
 /* ---- micro-benchmarks of the sm_100a building blocks (tools/ubench.py only) -------------------

@@ -13,6 +13,7 @@ if [ "$1" != "multi" ]; then
     done
   done
   cat gpurun_out/ubench.txt
+  timeout 120 python tools/probe_pair.py > gpurun_out/probe_pair.txt 2>&1; cat gpurun_out/probe_pair.txt
   # 1. full parity suite incl. the head_dim-64 (C1) tests that have not run on a GPU yet
   timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.txt 2>&1; tail -3 gpurun_out/pytest_gpu.txt
   # 2. the CTA-pair forward variants under the forward + API tests (gate for switching the default)
