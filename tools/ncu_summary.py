@@ -19,7 +19,15 @@ KEEP = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sectors_op_red.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
-        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        # the shared-memory data pipe (128 B wavefront per clk and SM) is shared by MMA operand fetch (tc) and
+        # the LSU: their sum is the number to watch (profiles/README.md, "What the captures say")
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size"]
 for r in rows[2:]:
     print("==", r[hdr.index("Kernel Name")][:70])
@@ -40,3 +48,17 @@ for i in sorted(sorted(range(len(data)), key=lambda i: -int(data[i][isamp]))[:to
     r = data[i]
     st = sorted(((int(r[c]), x[6:]) for c, x in stall if int(r[c]) > 0), reverse=True)[:2]
     print(f"{i:5d} {100 * int(r[isamp]) / tot:5.1f}% ex={r[iex]:>10s} {r[isrc].strip()[:58]:58s} {st}")
+# shared-memory wavefronts by opcode (LSU-visible part; TMA / mbarrier traffic is only in the raw totals)
+if "L1 Wavefronts Shared" in h:
+    iw = h.index("L1 Wavefronts Shared")
+    agg = {}
+    for r in data:
+        if r[iw].isdigit() and int(r[iw]) > 0:
+            words = r[isrc].split()
+            op = words[1] if words[0].startswith("@") else words[0]
+            a = agg.setdefault(op, [0, 0])
+            a[0] += int(r[iw])
+            a[1] += int(r[iex])
+    print("shared-memory wavefronts by opcode:")
+    for op, (w, x) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:8]:
+        print(f"   {op:16s} wavefronts {w:14d}  instructions {x:12d}  ({w / max(x, 1):.1f} per instruction)")
