@@ -43,6 +43,21 @@ def test_normal_layout_flash_none():
         torch.testing.assert_close(p(g).double(), r, **TOL[torch.bfloat16])
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_flash_triton_noncausal(dtype):
+    """flash="triton" (reference: inter_flash_attn_triton / _backward_triton, burst_utils.py:103-146) selects the
+    same sm_100a tile kernels in the flash layout [B,S,N,H]; non-causal is the only mode the reference allows."""
+    torch.manual_seed(2)
+    b, s, n, d = 2, 384, 4, 128
+    q, k, v, do = (torch.randn(b, s, n, d, device="cuda", dtype=dtype) for _ in range(4))
+    qq, kk, vv = (t.clone().requires_grad_() for t in (q, k, v))
+    o = burst_attn_func(qq, kk, vv, None, "triton", False, True)
+    dq, dk, dv = torch.autograd.grad(o, (qq, kk, vv), do)
+    o_ref, _, dq_ref, dk_ref, dv_ref = orc.dense_attention_bwd(q.cpu(), k.cpu(), v.cpu(), do.cpu())
+    for g, r in ((o, o_ref), (dv, dv_ref), (dk, dk_ref), (dq, dq_ref)):
+        torch.testing.assert_close(g.double().cpu(), r, **TOL[dtype])
+
+
 def test_causal_requires_cuda_flash_like_reference():
     q = torch.randn(1, 128, 1, 128, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(AssertionError):
