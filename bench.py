@@ -98,68 +98,232 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- #
-def cpu_port_step(S, threads):
-    """One fwd+bwd of the reference's path restated by oracle/ (4 simulated ring
-    rounds, fp32, torch CPU kernels on `threads` host threads).  Returns seconds."""
+def _ref_shim():
+    """baseline/ref_shim.py: the UNMODIFIED reference from the git-ignored baseline/_ref (None if that install did
+    not travel to this box)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    try:
+        import ref_shim
+        if ref_shim.available():
+            ref_shim.load()
+            return ref_shim
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write(f"bench.py: reference in baseline/_ref not usable ({e!r}); CPU arm falls back to the oracle port\n")
+    return None
+
+
+def cpu_ref_step(shim, S, Hc, Dc, dtype, W, threads):
+    """One fwd+bwd of the reference's own device-agnostic chunk path (inter_normal_attn / _backward,
+    burst_utils.py:42-100) over a W-rank ring simulated on the host cores.  Returns (s_fwd, s_bwd, flops_fwd)."""
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    q, k, v, do = (torch.randn(1, Hc, S, Dc, generator=g).to(dtype) for _ in range(4))
+    *_, tf, tb = shim.cpu_ring_step(q, k, v, do, W, Dc ** -0.5)
+    return tf, tb, 4.0 * S * S * Hc * Dc
+
+
+def cpu_port_step(S, threads, Hc=8, Dc=D):
+    """Fallback when baseline/_ref is absent: the oracle's restatement of the same path (4 simulated ring
+    rounds, fp32).  Returns (s_fwd+bwd, flops_fwd+bwd)."""
     from oracle import attention_oracle as orc
     torch.set_num_threads(threads)
     g = torch.Generator().manual_seed(0)
-    W, Hc = 4, 8
-    q, k, v, do = (torch.randn(1, S, Hc, D, generator=g) for _ in range(4))
+    W = 4
+    q, k, v, do = (torch.randn(1, S, Hc, Dc, generator=g) for _ in range(4))
     sh = lambda t: [orc.shard(t, r, W, "contiguous") for r in range(W)]
     qs, ks, vs, dos = sh(q), sh(k), sh(v), sh(do)
     t0 = time.time()
-    os_, lses = orc.ring_forward(qs, ks, vs, D ** -0.5, "none", torch.float32)
-    orc.ring_backward(qs, ks, vs, os_, lses, dos, D ** -0.5, "none", torch.float32)
+    os_, lses = orc.ring_forward(qs, ks, vs, Dc ** -0.5, "none", torch.float32)
+    orc.ring_backward(qs, ks, vs, os_, lses, dos, Dc ** -0.5, "none", torch.float32)
     dt = time.time() - t0
-    return dt, 3.5 * 4.0 * S * S * Hc * D
+    return dt, 3.5 * 4.0 * S * S * Hc * Dc
 
 
-def best_cpu_threads():
-    """torch's CPU kernels do not scale to every hardware thread of a big host on these shapes (128
-    threads were 10x slower than 8 here); probe a few thread counts on a small sample and keep the best."""
+def best_cpu_threads(shim):
+    """torch's CPU kernels do not scale to every hardware thread of a big host on these shapes (128 threads
+    were 10x slower than 8 on the round-1 box); probe a few thread counts on a small sample and keep the best."""
     n = os.cpu_count() or 1
     best, best_rate = n, 0.0
-    for t in sorted({n, min(n, 64), min(n, 32), min(n, 16)}, reverse=True):
-        cpu_port_step(512, t)
-        dt, fl = cpu_port_step(2048, t)
-        if fl / dt > best_rate:
-            best, best_rate = t, fl / dt
+    for t in sorted({n, min(n, 64), min(n, 32), min(n, 16), min(n, 8)}, reverse=True):
+        if shim is not None:
+            cpu_ref_step(shim, 512, 8, 64, torch.float32, 1, t)
+            tf, tb, fl = cpu_ref_step(shim, 2048, 8, 64, torch.float32, 1, t)
+            rate = 3.5 * fl / (tf + tb)
+        else:
+            cpu_port_step(512, t)
+            dt, fl = cpu_port_step(2048, t)
+            rate = fl / dt
+        if rate > best_rate:
+            best, best_rate = t, rate
     return best
 
 
-def cpu_baseline(S=6144):
-    threads = best_cpu_threads()
-    dt, fl = cpu_port_step(S, threads)
-    return {"value": fl / dt / 1e12, "unit": "TFLOPS/s", "cores": threads, "kind": "port",
-            "sample": f"oracle port (torch CPU fp32), fwd+bwd, bs=1 S={S} H=8 d=128, 4 simulated ring rounds, "
-                      f"{dt:.1f} s"}
+def cpu_baseline():
+    """BASELINE.json configs[0] (C1): bs=1 seq=4096 H=8 d=64, the reference's CPU-runnable case, through the
+    reference's own functions, fp32 and bf16, W in {1, 4} simulated ranks: 1 warm-up + 3 timed reps."""
+    shim = _ref_shim()
+    threads = best_cpu_threads(shim)
+    if shim is None:
+        dt, fl = cpu_port_step(4096, threads, 8, 64)
+        return {"value": fl / dt / 1e12, "unit": "TFLOPS/s", "cores": threads, "kind": "port",
+                "sample": f"oracle port (torch CPU fp32) of the reference path, C1: fwd+bwd bs=1 S=4096 H=8 d=64, "
+                          f"4 simulated ring rounds, {dt:.1f} s (baseline/_ref absent on this box)"}
+    S, Hc, Dc = 4096, 8, 64
+    detail = {}
+    t_all = time.time()
+    for dtype, name in ((torch.float32, "fp32"), (torch.bfloat16, "bf16")):
+        for W in (1, 4):
+            cpu_ref_step(shim, S, Hc, Dc, dtype, W, threads)
+            tf = tb = 0.0
+            for _ in range(3):
+                a, b, fl = cpu_ref_step(shim, S, Hc, Dc, dtype, W, threads)
+                tf, tb = tf + a / 3, tb + b / 3
+            detail[f"{name}_W{W}"] = {"fwd_ms": 1e3 * tf, "bwd_ms": 1e3 * tb, "fwd_gflops": fl / tf / 1e9,
+                                      "bwd_gflops": 2.5 * fl / tb / 1e9, "fwd_bwd_gflops": 3.5 * fl / (tf + tb) / 1e9}
+    main = detail["fp32_W4"]
+    return {"value": main["fwd_bwd_gflops"] / 1e3, "unit": "TFLOPS/s", "cores": threads,
+            "host_threads_available": os.cpu_count(), "kind": "reference",
+            "sample": "reference inter_normal_attn/_backward (burst_utils.py:42-100, unmodified, from baseline/_ref) on the "
+                      f"host cores, C1: bs=1 S=4096 H=8 d=64, fwd+bwd; value = fp32, 4 simulated ring ranks; 1 warm-up + "
+                      f"3 reps per cell, {time.time() - t_all:.1f} s in total",
+            "detail_gflops": detail}
 
 
 def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores, on a BOUNDED
+    sample of the bench workload (same d=128, bf16, non-causal; H=8 instead of 32, S=4096 instead of 262144)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = best_cpu_threads()
-    S = 4096
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_port_step(S, threads)
+    shim = _ref_shim()
+    threads = best_cpu_threads(shim)
+    S, Hc = 4096, 8
+    warm = max(0, min(args.warmup, 1))
     steps = max(1, min(args.steps, 5))
     t = 0.0
-    for _ in range(steps):
-        dt, fl = cpu_port_step(S, threads)
-        t += dt
+    if shim is not None:
+        for _ in range(warm):
+            cpu_ref_step(shim, S, Hc, D, torch.bfloat16, 4, threads)
+        for _ in range(steps):
+            tf, tb, fl1 = cpu_ref_step(shim, S, Hc, D, torch.bfloat16, 4, threads)
+            t += tf + tb
+        fl, kind, dt_name = 3.5 * fl1, "reference", "bf16"
+        what = ("reference inter_normal_attn/_backward (burst_utils.py:42-100, unmodified, baseline/_ref), torch CPU bf16, "
+                f"{threads} threads")
+    else:
+        for _ in range(warm):
+            cpu_port_step(S, threads)
+        for _ in range(steps):
+            dt, fl = cpu_port_step(S, threads)
+            t += dt
+        kind, dt_name = "port", "f32"
+        what = f"oracle port of the reference path (torch CPU fp32, {threads} threads; baseline/_ref absent)"
     val = fl * steps / t / 1e12
-    sample = (f"oracle port of the reference path (torch CPU fp32, {threads} threads): fwd+bwd bs=1 S={S} H=8 d=128, "
-              f"4 simulated ring rounds per step")
+    sample = f"{what}: fwd+bwd bs=1 S={S} H={Hc} d=128 non-causal, 4 simulated ring ranks per step"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "TFLOPS/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t / steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * t / steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": dt_name, "data": "synthetic",
         "config": {"workload": "bounded CPU sample of the bench workload: " + sample},
-        "cpu_baseline": {"value": val, "unit": "TFLOPS/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "TFLOPS/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "TFLOPS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# --------------------------------------------------------------------------- #
+# ring parity before timing: the reference's own protocol (test/test_burst.py:159-219: b=2, s=256*W, d=128, fp16
+# rtol=1e-3/atol=1e-2; bf16 at this repo's stated rtol=1.6e-2/atol=2e-2) for non-causal / zigzag / striped shards,
+# fwd + bwd, against a PLAIN PyTorch fp32 dense attention computed on the GPU (the oracle is not used here).
+# --------------------------------------------------------------------------- #
+def _shard(t, rank, world, layout):
+    if layout == "contiguous":
+        return t.chunk(world, dim=1)[rank].contiguous()
+    if layout == "zigzag":  # halves {i, 2W-1-i} (reference test/test_burst.py:46-52)
+        c = t.chunk(2 * world, dim=1)
+        return torch.cat([c[rank], c[2 * world - 1 - rank]], dim=1).contiguous()
+    return t[:, rank::world].contiguous()  # striped: tokens {i, i+W, ...} (:55-58)
+
+
+def _dense_fp32(q, k, v, do, causal):
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        q, k, v = (t.float().permute(0, 2, 1, 3).detach().requires_grad_() for t in (q, k, v))
+        s = (q @ k.transpose(-1, -2)) * q.shape[-1] ** -0.5
+        if causal:
+            S = s.shape[-1]
+            s = s.masked_fill(~torch.ones(S, S, dtype=torch.bool, device=s.device).tril(), float("-inf"))
+        o = torch.softmax(s, -1) @ v
+        g = torch.autograd.grad(o, (q, k, v), do.float().permute(0, 2, 1, 3))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return [t.permute(0, 2, 1, 3) for t in (o, *g)]
+
+
+def ring_parity(world, rank, dev, double_group):
+    from burst_attn import burst_attn_func, burst_attn_func_striped
+    cases, failed, worst = 0, [], 0.0
+    for dtype, tol in ((torch.float16, (1e-3, 1e-2)), (torch.bfloat16, (1.6e-2, 2e-2))):
+        for name, func, causal, layout in (("none", burst_attn_func, False, "contiguous"),
+                                           ("zigzag", burst_attn_func, True, "zigzag"),
+                                           ("striped", burst_attn_func_striped, True, "striped")):
+            g = torch.Generator().manual_seed(7)  # identical full tensors on every rank
+            q, k, v, do = (torch.randn(2, 256 * world, 8, D, generator=g).to(dtype).to(dev) for _ in range(4))
+            ref = _dense_fp32(q, k, v, do, causal)
+            ql, kl, vl = (_shard(t, rank, world, layout).requires_grad_() for t in (q, k, v))
+            o = func(ql, kl, vl, None, "cuda", causal, True, False, None, double_group)
+            grads = torch.autograd.grad(o, (ql, kl, vl), _shard(do, rank, world, layout))
+            ok = True
+            for got, r in zip((o, *grads), ref):
+                r = _shard(r, rank, world, layout)
+                err = (got.float() - r).abs()
+                ok &= bool((err <= tol[1] + tol[0] * r.abs()).all().item())
+                worst = max(worst, float(err.max().item()))
+            flag = torch.tensor([0 if ok else 1], device=dev)
+            if world > 1:
+                dist.all_reduce(flag)
+            cases += 1
+            if flag.item() != 0:
+                failed.append(f"{name}/{str(dtype).split('.')[-1]}")
+    w = torch.tensor([worst], device=dev)
+    if world > 1:
+        dist.all_reduce(w, op=dist.ReduceOp.MAX)
+    return {"W": world, "protocol": "b=2 s=256*W h=8 d=128; none/zigzag/striped x fp16 (rtol 1e-3, atol 1e-2) / bf16 "
+            "(1.6e-2, 2e-2); O,dQ,dK,dV vs plain PyTorch fp32 dense attention on the GPU",
+            "cases": cases, "ok": not failed, "failed": failed, "max_abs_err": float(w.item())}
+
+
+def ref_ratio(world, S, causal, value):
+    """value / the UNMODIFIED reference's fwd+bwd TFLOPS/s on the same kind of box at the same (N, S, causal), as
+    measured by tools/ref_on_b200.py and committed in profiles/ref_on_b200_r02.json (None if not measured)."""
+    path = os.path.join(ROOT, "profiles", "ref_on_b200_r02.json")
+    if not os.path.exists(path):
+        return None
+    for ln in open(path):
+        try:
+            r = json.loads(ln)
+        except Exception:  # noqa: BLE001
+            continue
+        if r.get("n_gpus") == world and r.get("seq") == S and bool(r.get("causal")) == bool(causal):
+            return {"ratio": value / r["fwd_bwd_tflops"], "reference_tflops": r["fwd_bwd_tflops"],
+                    "source": "profiles/ref_on_b200_r02.json (tools/ref_on_b200.py, separate box of the same pool)"}
+    return None
+
+
+def ncu_traffic(kernel, Sq, Sk, Hh, causal):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of `kernel` at this launch shape from the
+    ncu --set full summary that tools/profile.sh regenerates (profiles/ncu_traffic.json); None when that shape was
+    never captured -- never a literal."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    try:
+        tab = json.load(open(path))
+    except Exception:  # noqa: BLE001
+        return None, None
+    key = f"{kernel}:Sq={Sq}:Sk={Sk}:H={Hh}:causal={int(bool(causal))}"
+    ent = tab.get(key)
+    return (ent["dram_bytes"], ent.get("source")) if ent else (None, None)
 
 
 # --------------------------------------------------------------------------- #
@@ -173,6 +337,10 @@ def main():
     ap.add_argument("--causal", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the ring parity protocol that runs before timing")
+    ap.add_argument("--ab-comm", action="store_true",
+                    help="also time the step with the ring replaced by a local buffer swap (BA_RING_TRANSPORT=local): "
+                         "the A/B partner that isolates exposed ring-communication time")
     ap.add_argument("--configs", default="", help="comma list of extra runs in the same process group, e.g. "
                     "'262144,524288c,1048576' (c = causal zigzag); one JSON line each (multi-GPU sessions are "
                     "expensive to start)")
@@ -205,11 +373,13 @@ def main():
     args.double_group = [None, None]
     if args.double_ring and world > 1:
         L = args.double_ring
+        os.environ["BA_DOUBLE_RING"] = "1"
         assert world % L == 0 and 1 < L < world, "--double-ring L needs 1 < L < world and L | world"
         rows = [list(range(n * L, (n + 1) * L)) for n in range(world // L)]
         mk_groups = lambda ranks: dist.new_subgroups_by_enumeration(ranks, backend="nccl")[0]  # noqa: E731
         args.double_group = [mk_groups(rows), mk_groups([list(c) for c in zip(*rows)])]
 
+    args.parity = None if args.no_parity else ring_parity(world, rank, dev, args.double_group)
     runs = [(args.seq, args.causal, B)]
     if args.configs:  # "<seq>[c][b<batch>]", e.g. 262144, 524288c, 65536b4 (the reference README's two sweeps)
         import re
@@ -224,6 +394,8 @@ def main():
         torch.cuda.empty_cache()
     if world > 1:
         dist.barrier()
+        from burst_attn import comm as _comm
+        _comm.destroy_rings()
         dist.destroy_process_group()
 
 
@@ -299,12 +471,15 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
         # 10*Sq*Sk*H*D per round) / launches per step; non-causal: exactly 10*S_loc^2*H*D per ring round
         fl_launch = flops(S, "bwd", Bn) / causal_div / world / (n_l / K)
         ach = fl_launch / (tot_ms / n_l * 1e-3) / 1e12
-        # DRAM traffic per launch from the committed ncu --set full capture (profiles/ncu_bwd_r01_final.txt:
-        # dram__bytes_read 2.863 GB + write 1.771 GB) -- valid for the launch shape it was taken on
-        # (Sq = Sk = 32768 per launch, H=32, non-causal: every multi-GPU ring round at S_local=32768)
-        traffic = 4.634e9 if (S_loc == 32768 and Bn == 1 and not args.causal and n_l == K * world) else None
+        # DRAM traffic per launch: read from the per-shape ncu --set full summary tools/profile.sh regenerates
+        # (profiles/ncu_traffic.json), for the launch shape this run actually used; None if never captured
+        shp = ops.dominant_shape("bwd_chunk_kernel")
+        traffic, traffic_src = ncu_traffic("bwd_chunk_kernel", *shp) if shp else (None, None)
         roof = {"kernel": "bwd_chunk_kernel", "bound": "tensor", "achieved": ach, "peak": pk["sustained"],
-                "unit": "TFLOP/s", "frac": ach / pk["sustained"], "traffic": traffic,
+                "unit": "TFLOP/s", "frac": ach / pk["sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                "launch_shape": {"Sq": shp[0], "Sk": shp[1], "H": shp[2], "causal": shp[3]} if shp else None,
+                "algorithmic_bytes": (2 * shp[0] + 2 * shp[1]) * shp[2] * D * 2 * Bn + (shp[0] + 2 * shp[1]) * shp[2] * D * 4 * 2 * Bn
+                if shp else None,
                 "peak_source": pk["source"] + " bf16_tflops_sustained (of measured)",
                 "launches": n_l, "avg_launch_ms": tot_ms / n_l}
         if "fwd_chunk_kernel" in kms:
@@ -330,16 +505,49 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
         hq, hk, hv, hdo = (t.cpu().pin_memory() for t in (q, k, v, do))
         ho = [torch.empty_like(hq).pin_memory() for _ in range(4)]
 
+        copy_s = torch.cuda.Stream(device=dev)
+
         def e2e_step():
-            dq_, dk_, dv_, ddo_ = (h.to(dev, non_blocking=True) for h in (hq, hk, hv, hdo))
-            outs = step(dq_, dk_, dv_, ddo_)
-            for h, t in zip(ho, outs):
+            # what a user of the public API can overlap with streams: dO rides up under the forward, O rides down
+            # under the backward; Q/K/V up and dQ/dK/dV down stay exposed (the drivers take whole device tensors)
+            cur = torch.cuda.current_stream(dev)
+            dq_, dk_, dv_ = (h.to(dev, non_blocking=True) for h in (hq, hk, hv))
+            with torch.cuda.stream(copy_s):
+                ddo_ = hdo.to(dev, non_blocking=True)
+                ev_do = torch.cuda.Event()
+                ev_do.record(copy_s)
+            ddo_.record_stream(cur)
+            qq, kk, vv = dq_.requires_grad_(), dk_.requires_grad_(), dv_.requires_grad_()
+            o = burst_attn_func(qq, kk, vv, None, "cuda", args.causal, True, False, None, args.double_group)
+            ev_o = torch.cuda.Event()
+            ev_o.record(cur)
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(ev_o)
+                ho[0].copy_(o.detach(), non_blocking=True)
+            o.record_stream(copy_s)
+            cur.wait_event(ev_do)
+            grads = torch.autograd.grad(o, (qq, kk, vv), ddo_)
+            for h, t in zip(ho[1:], grads):
                 h.copy_(t, non_blocking=True)
+            cur.wait_stream(copy_s)
         e2e_step()
         ms_e2e = timed(e2e_step, K)
         nbytes = hq.numel() * hq.element_size()
         e2e = {"value": fl_step / (ms_e2e * 1e-3) / 1e12, "unit": "TFLOPS/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": 4 * nbytes * world, "d2h_bytes_per_step": 4 * nbytes * world}
+
+    # ---- A/B: the same step with the ring replaced by a local buffer swap -> exposed ring-communication time
+    ab = None
+    if args.ab_comm and world > 1:
+        os.environ["BA_RING_TRANSPORT"] = "local"
+        try:
+            step(q, k, v, do)
+            ms_local = timed(lambda: step(q, k, v, do), K)
+        finally:
+            os.environ.pop("BA_RING_TRANSPORT", None)
+        ab = {"ms_per_step_ring": ms_step, "ms_per_step_local_swap": ms_local,
+              "exposed_comm_frac": max(0.0, (ms_step - ms_local) / ms_step),
+              "how": "BA_RING_TRANSPORT=local: every hop is a device-local copy src->dst on the compute stream"}
 
     tot_launch = torch.tensor([launches], device=dev, dtype=torch.int64)
     if world > 1:
@@ -361,7 +569,8 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
                        "l2": "inputs (>= 256 MiB per tensor per rank) exceed the 126 MB L2; no flush needed"},
             "value_per_gpu": value / world, "fwd_tflops": fwd_tflops, "fwd_ms": ms_fwd,
             "gpu_launches": int(tot_launch.item()), "clocks": clocks, "e2e": e2e, "roofline": roof, "overlap": overlap,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "parity": getattr(args, "parity", None), "comm_ab": ab,
+            "vs_reference_on_b200": ref_ratio(world, S, args.causal, value),
         }
         print(json.dumps(line), flush=True)
 

@@ -30,6 +30,24 @@ __all__ = ["burst_attn_func", "burst_attn_func_striped", "OpBurstAttn", "OpBurst
            "get_partition_id", "split2_gethalf"]
 
 
+class _Range:
+    """NVTX range per ring round (BA_NVTX=1): `ncu --nvtx --nvtx-include "bwd_round_3/"` or a timeline tool then
+    sees the post / kernel / wait of one round as a unit.  A no-op otherwise."""
+    on = os.environ.get("BA_NVTX", "0") == "1"
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _Range.on:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _Range.on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def get_partition_id(double_group, r):
     """Reference :20-37.  Single ring (``double_group[0] is None``): the OFFSET ``r - 1`` of the held shard
     behind this rank.  Double ring: the RANK ID of the held shard, ``W = L*M``, rank ``= inter*L + intra``:
@@ -39,6 +57,11 @@ def get_partition_id(double_group, r):
     L, M = get_world_size(double_group[0]), get_world_size(double_group[1])
     b, a = get_rank(double_group[0]), get_rank(double_group[1])
     return ((a - (r - 1) // L) % M) * L + (b - (r - 1) % L) % L
+
+
+# Hierarchical ring over NCCL: opt-in until `RING_CHECK_DOUBLE=<L> torchrun tests/ring_check.py` has passed on
+# GPUs (the flat ring over process_group is always correct); flipped to "1" once profiles/ holds that log.
+_DOUBLE_RING_DEFAULT = "0"
 
 
 class _Topology:
@@ -57,7 +80,7 @@ class _Topology:
         self.intra, self.inter = intra, inter
         self.L, self.M = self.W, 1
         self.hier = False
-        if intra is not None and inter is not None and os.environ.get("BA_DOUBLE_RING", "1") != "0":
+        if intra is not None and inter is not None and os.environ.get("BA_DOUBLE_RING", _DOUBLE_RING_DEFAULT) != "0":
             L, M = get_world_size(intra), get_world_size(inter)
             if 1 < L < self.W:  # reference comm.py:215-219: a ring that is all-intra (or all-inter) is flat
                 assert L * M == self.W, f"double ring: intra size {L} x inter size {M} != world {self.W}"
@@ -205,13 +228,14 @@ def _ring_forward(q, k, v, scale, seq_dim, mode, topo):
     cur_k, cur_v = k, v
     for r in range(1, W + 1):
         j = topo.source(r)  # source rank of the held K/V (App. B)
-        if r != W:
-            nxt = recv[(r - 1) % len(recv)]
-            ring.post([cur_k, cur_v], nxt)
-        _fwd_dispatch(ops, mode, r, W, i, j, q, cur_k, cur_v, o_acc, lse, out, scale, seq_dim)
-        if r != W:
-            ring.wait()
-            cur_k, cur_v = nxt
+        with _Range(f"fwd_round_{r}"):
+            if r != W:
+                nxt = recv[(r - 1) % len(recv)]
+                ring.post([cur_k, cur_v], nxt)
+            _fwd_dispatch(ops, mode, r, W, i, j, q, cur_k, cur_v, o_acc, lse, out, scale, seq_dim)
+            if r != W:
+                ring.wait()
+                cur_k, cur_v = nxt
     return out, lse
 
 
@@ -330,11 +354,12 @@ def _ring_backward(d_o, q, k, v, out, lse, scale, seq_dim, mode, topo, determini
                 inbound = spare.pop()
                 srcs.append(hold)
                 dsts.append(inbound)
-            if srcs:
-                ring.post(srcs, dsts)
-            round_kernel(r, j, bundle, part)
-            if srcs:
-                ring.wait()
+            with _Range(f"bwd_round_{r}"):
+                if srcs:
+                    ring.post(srcs, dsts)
+                round_kernel(r, j, bundle, part)
+                if srcs:
+                    ring.wait()
             if r != W:
                 bundle = nxt
             if r == 1:

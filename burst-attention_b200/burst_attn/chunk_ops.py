@@ -30,10 +30,12 @@ class NativeOps:
         self.lib = _n.lib()  # raises if the library is missing -- no fallback
         self.launches = 0    # kernels launched through this object (bench.py's gpu_launches)
         self.timing = None   # bench.py: {kernel name: [(start_event, end_event), ...]} when enabled
+        self.shapes = {}
 
     def enable_timing(self, on=True):
         """Bracket every launch with CUDA events on the launching stream (bench.py roofline)."""
         self.timing = {} if on else None
+        self.shapes = {}  # {kernel name: {(Sq, Sk, H, causal): launches}} while timing is on
 
     def _t0(self, dev):
         if self.timing is None:
@@ -47,6 +49,17 @@ class NativeOps:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record(torch.cuda.current_stream(dev))
             self.timing.setdefault(name, []).append((e0, e1))
+
+    def _shape(self, name, Sq, Sk, H, causal):
+        if self.timing is not None:
+            d = self.shapes.setdefault(name, {})
+            key = (int(Sq), int(Sk), int(H), bool(causal))
+            d[key] = d.get(key, 0) + 1
+
+    def dominant_shape(self, name):
+        """(Sq, Sk, H, causal) of most launches of `name` since enable_timing (bench.py: ncu traffic lookup)."""
+        d = self.shapes.get(name)
+        return max(d, key=d.get) if d else None
 
     def kernel_ms(self):
         """{kernel name: (launches, total ms)} -- call after a synchronize."""
@@ -64,6 +77,7 @@ class NativeOps:
             _n.BA_MASK_CAUSAL if causal else _n.BA_MASK_NONE, int(causal_offset), flags,
             _n.dtype_code(q.dtype), _n.stream_ptr(q.device))
         _n.check(rc, "ba_fwd_chunk")
+        self._shape("fwd_chunk_kernel", Sq, Sk, H, causal)
         self._t1("fwd_chunk_kernel", e0, q.device)
         self.launches += 1
 
@@ -89,6 +103,7 @@ class NativeOps:
             _n.BA_MASK_CAUSAL if causal else _n.BA_MASK_NONE, int(causal_offset), 1 if deterministic else 0,
             _n.dtype_code(q.dtype), _n.stream_ptr(q.device))
         _n.check(rc, "ba_bwd_chunk")
+        self._shape("bwd_chunk_kernel", Sq, Sk, H, causal)
         self._t1("bwd_chunk_kernel", e0, q.device)
         self.launches += 1
 

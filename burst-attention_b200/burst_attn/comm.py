@@ -151,16 +151,41 @@ class _NativeRing:
         return self.arena[off:off + nbytes].view(dtype).view(shape)
 
 
-_native_rings: Dict[Tuple[int, str, int, str], _NativeRing] = {}
+_native_rings: Dict[tuple, _NativeRing] = {}
+
+
+def _group_identity(group) -> tuple:
+    """A stable identity of a process group: its name and member ranks (NOT id(group): after a group is
+    destroyed a new one can reuse the address and would silently inherit a communicator with stale peers)."""
+    if group is None:
+        return ("world", get_world_size(None))
+    try:
+        return (str(getattr(group, "group_name", "")), tuple(dist.get_process_group_ranks(group)))
+    except Exception:
+        return ("id", id(group))
 
 
 def _native_ring(group, tag: str, device: torch.device, transport: str = "nccl") -> _NativeRing:
-    key = (id(group) if group is not None else 0, tag, device.index if device.index is not None else -1, transport)
+    key = (_group_identity(group), tag, device.index if device.index is not None else -1, transport)
     ring = _native_rings.get(key)
     if ring is None:
         ring = _NativeRing(group, tag, device, transport)
         _native_rings[key] = ring
     return ring
+
+
+def destroy_rings() -> None:
+    """Tear down every cached native ring (communicator, side stream, copy-engine arena).  Call it before
+    ``dist.destroy_process_group()`` -- e.g. on elastic restarts -- so that a later re-init builds fresh
+    communicators; all ranks must call it (device-synchronised) together."""
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    for ring in _native_rings.values():
+        ring.arena = None
+        if ring.handle:
+            ring.lib.ba_ring_destroy(ring.handle)
+            ring.handle = ctypes.c_void_p()
+    _native_rings.clear()
 
 
 # --------------------------------------------------------------------------- #
@@ -171,7 +196,11 @@ class Ring:
                  transport: Optional[str] = None):
         self.comm = process_group
         self.transport = transport or os.environ.get("BA_RING_TRANSPORT", "nccl")
-        assert self.transport in ("nccl", "ce"), f"BA_RING_TRANSPORT must be nccl or ce, got {self.transport!r}"
+        # "local": measurement only (bench.py --ab-comm): every hop becomes a device-local copy src -> dst on the
+        # compute stream, i.e. the ring is replaced by a local buffer swap -- same kernels, same bytes through HBM,
+        # nothing over NVLink -- the A/B partner that isolates exposed communication time (results are wrong)
+        assert self.transport in ("nccl", "ce", "local"), \
+            f"BA_RING_TRANSPORT must be nccl, ce or local, got {self.transport!r}"
         self.world_size = get_world_size(process_group)
         self.rank = get_rank(process_group)
         self.tag = tag or ("dq" if dq else "kv")
@@ -202,7 +231,11 @@ class Ring:
         srcs = [s for s, _ in self._pending]
         dsts = [d for _, d in self._pending]
         self._pending = []
-        if srcs[0].is_cuda:
+        if srcs[0].is_cuda and self.transport == "local":
+            for s, d in zip(srcs, dsts):
+                d.copy_(s)
+            self._reqs = []
+        elif srcs[0].is_cuda:
             self._device = srcs[0].device
             self._ensure_native(self._device)
             self._native.post(srcs, dsts)

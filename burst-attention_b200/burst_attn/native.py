@@ -42,8 +42,10 @@ _EXPORTS = (
     "ba_last_error", "ba_device_check", "ba_version", "ba_fwd_chunk", "ba_bwd_delta", "ba_bwd_chunk",
     "ba_cast_from_f32", "ba_accumulate_f32", "ba_ring_unique_id", "ba_ring_create", "ba_ring_post",
     "ba_ring_wait", "ba_ring_rank", "ba_ring_world", "ba_ring_destroy", "ba_ring_arena_create",
-    "ba_ring_arena_connect", "ba_selftest", "ba_ubench",
+    "ba_ring_arena_connect",
 )
+SELFTEST_LIB_PATH = os.path.join(os.path.dirname(LIB_PATH), "libburst_attn_b200_selftest.so")
+_SELFTEST_EXPORTS = ("ba_selftest_last_error", "ba_selftest", "ba_ubench")
 
 
 def exported_symbols() -> Sequence[str]:
@@ -95,12 +97,34 @@ def lib() -> ctypes.CDLL:
     L.ba_ring_arena_create.argtypes = [vp, ctypes.c_int64, ctypes.POINTER(vp), vp]
     L.ba_ring_arena_connect.restype = i
     L.ba_ring_arena_connect.argtypes = [vp, vp, vp]
-    L.ba_ubench.restype = i
-    L.ba_ubench.argtypes = [i, i, i, ctypes.POINTER(ctypes.c_int64), vp]
-    L.ba_selftest.restype = i
-    L.ba_selftest.argtypes = [i, vp, vp, vp, i, vp]
     _lib = L
     return L
+
+
+_selftest_lib = None
+
+
+def selftest_lib() -> ctypes.CDLL:
+    """The diagnostics library (include/burst_attn_b200_selftest.h); loaded by tests/ and tools/ only."""
+    global _selftest_lib
+    if _selftest_lib is None:
+        if not os.path.exists(SELFTEST_LIB_PATH):
+            raise NativeLibraryError(f"{SELFTEST_LIB_PATH} not found: build with __graft_entry__.build()")
+        L = ctypes.CDLL(SELFTEST_LIB_PATH)
+        i, vp = ctypes.c_int, ctypes.c_void_p
+        L.ba_selftest_last_error.restype = ctypes.c_char_p
+        L.ba_ubench.restype = i
+        L.ba_ubench.argtypes = [i, i, i, ctypes.POINTER(ctypes.c_int64), vp]
+        L.ba_selftest.restype = i
+        L.ba_selftest.argtypes = [i, vp, vp, vp, i, vp]
+        _selftest_lib = L
+    return _selftest_lib
+
+
+def check_selftest(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = selftest_lib().ba_selftest_last_error()
+        raise NativeLibraryError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
 
 
 def check(rc: int, what: str) -> None:

@@ -20,6 +20,9 @@
 // smem: K 32K, V 32K, Q 2x32K, dO 32K, dS 32K, dQ staging 2x16K, row stats 2x1K.
 #include <math.h>
 
+#include <mutex>
+#include <vector>
+
 #include "host_common.h"
 #include "sm100_ptx.cuh"
 
@@ -53,7 +56,8 @@ struct BwdParams {
   int B, Sq, Sk, H;
   float scale, scale_log2;
   int causal, causal_off;
-  int* sem;  // deterministic mode: [B][H][nQ] turn counters ordering the dQ reductions by key block; else null
+  int* sem;     // deterministic mode: [B][H][nQ] turn counters ordering the dQ reductions by key block; else null
+  int* ticket;  // deterministic mode: [B][H] key-block tickets (a CTA's key block = the order in which it STARTED)
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -71,6 +75,7 @@ struct __align__(8) BwdBarriers {
   uint64_t do_full, do_empty;
   uint64_t s_full, p_ready, dp_full, ds_ready, dq_full, dq_free, dkv_full;
   uint32_t tmem_base;
+  int key_block;  // deterministic mode: this CTA's ticket
 };
 
 // smem carve-up (bytes from the 1 KiB-aligned base)
@@ -105,7 +110,17 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
-  const int k0 = blockIdx.x * kTile;
+  // Key block of this CTA.  Deterministic mode orders the dQ reductions by key block and makes a CTA wait for
+  // all lower key blocks; to make that wait deadlock-free without assuming anything about the order in which
+  // the hardware dispatches blockIdx.x, the key block is a ticket drawn when the CTA starts: every lower
+  // ticket then belongs to a CTA that is already resident.
+  int kb = blockIdx.x;
+  if (p.sem) {
+    if (threadIdx.x == 0) bars->key_block = atomicAdd(p.ticket + b * p.H + h, 1);
+    __syncthreads();
+    kb = bars->key_block;
+  }
+  const int k0 = kb * kTile;
   const int nQ = (p.Sq + kTile - 1) / kTile;
   // first Q block that can see any key of this block: q >= k0 - off
   const int i_begin = p.causal ? max(0, k0 - p.causal_off) / kTile : 0;
@@ -307,11 +322,11 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->dq_free);
       // deterministic mode: the fp32 adds into dq_acc[q block] happen in key-block order.  Key blocks that
-      // see a given Q block are 0..x_max, and lower blockIdx.x are dispatched first, so waiting for our
-      // turn cannot deadlock.
+      // see a given Q block are 0..x_max and lower key blocks are tickets of CTAs that started earlier
+      // (see the top of the kernel), so waiting for our turn cannot deadlock.
       int* turn = p.sem ? p.sem + ((int64_t)b * p.H + h) * nQ + (i_begin + it) : nullptr;
       if (turn && issuer) {
-        while (ld_acquire_gpu(turn) != (int)blockIdx.x) __nanosleep(64);
+        while (ld_acquire_gpu(turn) != kb) __nanosleep(64);
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -338,7 +353,7 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (turn && issuer) {
         tma_store_wait<0>();  // our four reductions have been performed ...
         __threadfence();
-        st_release_gpu(turn, (int)blockIdx.x + 1);  // ... next key block's turn
+        st_release_gpu(turn, kb + 1);  // ... next key block's turn
       }
     }
     if (issuer) tma_store_wait<0>();
@@ -480,22 +495,38 @@ static int launch_bwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUte
   return BA_OK;
 }
 
-// one-time (grown on demand) workspace for the deterministic-mode turn counters
+// Deterministic-mode workspace (turn counters + tickets), one per (device, stream), grown on demand, zeroed on
+// the launching stream before every launch.  Launches on one stream are ordered, so they can share a
+// workspace; different streams / devices / host threads never do (a mutex guards the table).
+struct BwdWorkspace {
+  int device;
+  cudaStream_t stream;
+  int* ptr;
+  size_t cap;
+};
+static std::mutex g_ws_mutex;
+static std::vector<BwdWorkspace> g_ws;
+
 static int* bwd_sem_workspace(size_t n_ints, cudaStream_t stream) {
-  static int* ws = nullptr;
-  static size_t cap = 0;
-  static int ws_dev = -1;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-  if (ws == nullptr || cap < n_ints || ws_dev != dev) {
-    if (ws) cudaFree(ws);
-    ws = nullptr;
-    if (cudaMalloc(&ws, n_ints * sizeof(int)) != cudaSuccess) return nullptr;
-    cap = n_ints;
-    ws_dev = dev;
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  BwdWorkspace* w = nullptr;
+  for (auto& e : g_ws)
+    if (e.device == dev && e.stream == stream) w = &e;
+  if (!w) {
+    g_ws.push_back(BwdWorkspace{dev, stream, nullptr, 0});
+    w = &g_ws.back();
   }
-  if (cudaMemsetAsync(ws, 0, n_ints * sizeof(int), stream) != cudaSuccess) return nullptr;
-  return ws;
+  if (w->cap < n_ints) {
+    // the old buffer may still be in use by a launch in flight on this stream: free it in stream order
+    if (w->ptr && cudaFreeAsync(w->ptr, stream) != cudaSuccess) return nullptr;
+    w->ptr = nullptr, w->cap = 0;
+    if (cudaMallocAsync(reinterpret_cast<void**>(&w->ptr), n_ints * sizeof(int), stream) != cudaSuccess) return nullptr;
+    w->cap = n_ints;
+  }
+  if (cudaMemsetAsync(w->ptr, 0, n_ints * sizeof(int), stream) != cudaSuccess) return nullptr;
+  return w->ptr;
 }
 
 static bool f32_view_ok(const ba_tensor4& t) {
@@ -543,10 +574,12 @@ extern "C" int ba_bwd_chunk(ba_tensor4 d_o, ba_tensor4 q, ba_tensor4 k, ba_tenso
   p.causal = mask_mode == BA_MASK_CAUSAL;
   p.causal_off = causal_offset;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  p.sem = nullptr;
+  p.sem = p.ticket = nullptr;
   if (flags & BA_BWD_DETERMINISTIC) {
-    const size_t n = (size_t)B * H * ((Sq + kTile - 1) / kTile);
+    const size_t n_turn = (size_t)B * H * ((Sq + kTile - 1) / kTile);
+    const size_t n = n_turn + (size_t)B * H;
     p.sem = bwd_sem_workspace(n, st);
+    if (p.sem) p.ticket = p.sem + n_turn;
     if (!p.sem) {
       set_error("ba_bwd_chunk: could not allocate the deterministic-mode workspace (%zu ints)", n);
       return BA_ERR_CUDA;

@@ -1,4 +1,4 @@
-// Shared between the forward kernel variants (fwd_sm100.cu, fwd_pair_sm100.cu).
+// Constants and parameters of the forward tile kernel (fwd_sm100.cu).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -19,8 +19,6 @@ constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays <= 2^8
 
 struct FwdParams {
-  const uint16_t* q;  // raw 16-bit Q view (v3: rows are staged by the softmax threads into TMEM)
-  int64_t q_sb, q_ss, q_sh;
   float* o_acc;
   int64_t oacc_sb, oacc_ss, oacc_sh;
   float* lse;
@@ -35,13 +33,5 @@ struct FwdParams {
   int store_lowp;
 };
 
-
-// CTA-pair forward (fwd_pair_sm100.cu): opt-in, BA_FWD_IMPL=5
-int launch_fwd_pair(int dtype, const CUtensorMap& tmK64, const CUtensorMap& tmV, const FwdParams& p,
-                    cudaStream_t stream);
-
-// second CTA-pair variant (independent even/odd key streams per warpgroup): opt-in, BA_FWD_IMPL=6
-int launch_fwd_pair6(int dtype, const CUtensorMap& tmQ, const CUtensorMap& tmK64, const CUtensorMap& tmV,
-                     const FwdParams& p, cudaStream_t stream);
 
 }  // namespace ba

@@ -403,731 +403,6 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 
-// =====================================================================================================
-// v3: Q in TMEM.  Measured on B200 (profiles/): tcgen05.mma fetches its shared-memory operands at only
-// ~64 B/clk/SM, so an SS-form 128x128x16 MMA (8 KiB of A+B per 64 tensor cycles) runs at ~50 % of the
-// tensor rate and an N=64 one at ~33 %.  Here BOTH GEMMs are TS-form: the two Q tiles are staged once
-// per CTA into TMEM (the softmax threads read their own row from global and tcgen05.st it, the same
-// lane==row, 2 x 16-bit per column layout as P), so per MMA only the 2-4 KiB B operand (K or V sub-tile)
-// comes from shared memory.  The 64 KiB of smem Q used to occupy become a third K and V stage.
-// TMEM (512 cols): Q0 [0,64) Q1 [64,128) S0 [128,192) S1 [192,256) O0 [256,384) O1 [384,512);
-// S is 64 keys wide, single-buffered per Q tile; P aliases the first 32 columns of S.
-// =====================================================================================================
-constexpr int kStages3 = 3;
-constexpr uint32_t kOffK3 = 0;
-constexpr uint32_t kOffV3 = kStages3 * kTileBytes;
-constexpr uint32_t kOffBars3 = 2 * kStages3 * kTileBytes;
-constexpr int kFwd3SmemBytes = kOffBars3 + 256;
-
-struct __align__(8) Fwd3Barriers {
-  uint64_t k_full[kStages3], k_empty[kStages3];
-  uint64_t v_full[kStages3], v_empty[kStages3];
-  uint64_t q_ready[2];   // softmax -> MMA: Q_w staged in TMEM
-  uint64_t s_full[2];    // MMA -> softmax: S_w ready
-  uint64_t p_ready[2];   // softmax -> MMA: P_w written (and O_w rescaled)
-  uint64_t o_done[2];    // MMA -> softmax: PV accumulated (one completion per sub-tile)
-  uint64_t o_final[2];   // MMA -> softmax: last PV of this CTA completed
-  uint32_t tmem_base;
-};
-
-// QK^T of sub-tile jq (compile-time position U = jq % 6 -> K stage, half) for Q tile w
-template <bool kBF16, int U, int W>
-__device__ __forceinline__ void fwd3_issue_qk(uint32_t sb16) {
-  constexpr int st = (U >> 1) % kStages3, sub = U & 1;
-  constexpr uint32_t idesc = make_idesc(kBF16, kBlockM, kSub, false, false), hi = desc_hi(1024);
-  const uint32_t k_lo = sb16 + ((kOffK3 + st * kTileBytes + sub * kSub * 128) >> 4) + desc_lo_lbo(16);
-#pragma unroll
-  for (int kk = 0; kk < kHeadDim / 16; ++kk) {
-    const uint32_t off = ((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4;
-    umma_ts_lh(128 + W * 64, W * 64 + kk * 8, k_lo + off, hi, idesc, kk > 0 ? 1u : 0u);
-  }
-}
-template <bool kBF16, int U, int W>
-__device__ __forceinline__ void fwd3_issue_pv(uint32_t sb16, uint32_t acc) {
-  constexpr int st = (U >> 1) % kStages3, sub = U & 1;
-  constexpr uint32_t idesc = make_idesc(kBF16, kBlockM, kHeadDim, false, true), hi = desc_hi(1024);
-  const uint32_t v_lo = sb16 + ((kOffV3 + st * kTileBytes + sub * kSub * 128) >> 4) + desc_lo_lbo(kBoxBytes);
-#pragma unroll
-  for (int kk = 0; kk < kSub / 16; ++kk)
-    umma_ts_lh(256 + W * 128, 128 + W * 64 + kk * 8, v_lo + kk * (16 * 128 / 16), hi, idesc, kk > 0 ? 1u : acc);
-}
-
-// One sub-tile step of the MMA warp; U = j % 6 (3 K/V stages x 2 halves) is a compile-time constant.
-template <bool kBF16, int U>
-__device__ __forceinline__ void fwd3_mma_step(int j, uint32_t sb16, Fwd3Barriers* bars, int n_s0, int n_s1, int n_sub,
-                                              bool load_state) {
-  constexpr int st = (U >> 1) % kStages3, sub = U & 1;
-  constexpr int UN = (U + 1) % 6, stn = (UN >> 1) % kStages3, subn = UN & 1;
-  const int tile = j >> 1;
-  if (sub == 0) {
-    mbar_wait(&bars->v_full[st], (tile / kStages3) & 1);
-    tc_fence_after();
-  }
-  const bool next = (j + 1) < n_sub;
-  if (next && subn == 0) {
-    mbar_wait(&bars->k_full[stn], ((tile + 1) / kStages3) & 1);
-    tc_fence_after();
-  }
-  const uint32_t acc = (j > 0 || load_state) ? 1u : 0u;
-  if (j < n_s0) {
-    mbar_wait(&bars->p_ready[0], j & 1);
-    tc_fence_after();
-    fwd3_issue_pv<kBF16, U, 0>(sb16, acc);
-    umma_commit(&bars->o_done[0]);
-    if (j == n_s0 - 1) umma_commit(&bars->o_final[0]);
-  }
-  if (j + 1 < n_s0) {
-    fwd3_issue_qk<kBF16, UN, 0>(sb16);
-    umma_commit(&bars->s_full[0]);
-  }
-  if (j < n_s1) {
-    mbar_wait(&bars->p_ready[1], j & 1);
-    tc_fence_after();
-    fwd3_issue_pv<kBF16, U, 1>(sb16, acc);
-    umma_commit(&bars->o_done[1]);
-    if (j == n_s1 - 1) umma_commit(&bars->o_final[1]);
-  }
-  if (sub == 1) umma_commit(&bars->v_empty[st]);
-  if (j + 1 < n_s1) {
-    fwd3_issue_qk<kBF16, UN, 1>(sb16);
-    umma_commit(&bars->s_full[1]);
-  }
-  if (next && subn == 1) umma_commit(&bars->k_empty[stn]);
-}
-
-template <bool kBF16>
-__global__ void __launch_bounds__(kFwdThreads, 1)
-fwd3_chunk_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw;
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* sK = smem + kOffK3;
-  uint8_t* sV = smem + kOffV3;
-  Fwd3Barriers* bars = reinterpret_cast<Fwd3Barriers*>(smem + kOffBars3);
-
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-  const int lane = threadIdx.x & 31;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int row0 = (p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * (2 * kBlockM);
-  const int n_s0 = fwd_trip_count(row0, p);
-  const int n_s1 = fwd_trip_count(row0 + kBlockM, p);
-  const int n_sub = max(n_s0, n_s1);
-  const int n_tiles = (n_sub + 1) >> 1;
-
-  if (warp == 9 && lane == 0) {
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-  }
-  if (warp == 8) {
-    if (lane == 0) {
-      for (int i = 0; i < kStages3; ++i) {
-        mbar_init(&bars->k_full[i], 1);
-        mbar_init(&bars->k_empty[i], 1);
-        mbar_init(&bars->v_full[i], 1);
-        mbar_init(&bars->v_empty[i], 1);
-      }
-      for (int w = 0; w < 2; ++w) {
-        mbar_init(&bars->q_ready[w], 4);
-        mbar_init(&bars->s_full[w], 1);
-        mbar_init(&bars->p_ready[w], 4);
-        mbar_init(&bars->o_done[w], 1);
-        mbar_init(&bars->o_final[w], 1);
-      }
-      fence_mbar_init();
-    }
-    __syncwarp();
-    tmem_alloc(&bars->tmem_base, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (bars->tmem_base != 0) __trap();
-
-  if (warp == 9) {
-    // ============================================================ TMA producer (K/V only)
-    if (lane == 0) {
-      for (int i = 0; i < n_tiles; ++i) {
-        const int st = i % kStages3, ph = (i / kStages3) & 1;
-        mbar_wait(&bars->k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&bars->k_full[st], kTileBytes);
-        for (int half = 0; half < 2; ++half)
-          tma_load_4d(sK + st * kTileBytes + half * kBoxBytes, &tmK, &bars->k_full[st], half * 64, h, i * kBlockN, b);
-        mbar_wait(&bars->v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&bars->v_full[st], kTileBytes);
-        for (int half = 0; half < 2; ++half)
-          tma_load_4d(sV + st * kTileBytes + half * kBoxBytes, &tmV, &bars->v_full[st], half * 64, h, i * kBlockN, b);
-      }
-    }
-  } else if (warp == 8) {
-    // ============================================================ MMA issuer
-    const uint32_t sb16 = smem_u32(smem) >> 4;
-    if (n_sub > 0) {
-      mbar_wait(&bars->k_full[0], 0);
-      if (n_s0 > 0) {
-        mbar_wait(&bars->q_ready[0], 0);
-        tc_fence_after();
-        fwd3_issue_qk<kBF16, 0, 0>(sb16);
-        umma_commit(&bars->s_full[0]);
-      }
-      if (n_s1 > 0) {
-        mbar_wait(&bars->q_ready[1], 0);
-        tc_fence_after();
-        fwd3_issue_qk<kBF16, 0, 1>(sb16);
-        umma_commit(&bars->s_full[1]);
-      }
-    }
-    const bool ls = p.load_state != 0;
-    for (int j0 = 0; j0 < n_sub; j0 += 6) {
-      fwd3_mma_step<kBF16, 0>(j0, sb16, bars, n_s0, n_s1, n_sub, ls);
-      if (j0 + 1 < n_sub) fwd3_mma_step<kBF16, 1>(j0 + 1, sb16, bars, n_s0, n_s1, n_sub, ls);
-      if (j0 + 2 < n_sub) fwd3_mma_step<kBF16, 2>(j0 + 2, sb16, bars, n_s0, n_s1, n_sub, ls);
-      if (j0 + 3 < n_sub) fwd3_mma_step<kBF16, 3>(j0 + 3, sb16, bars, n_s0, n_s1, n_sub, ls);
-      if (j0 + 4 < n_sub) fwd3_mma_step<kBF16, 4>(j0 + 4, sb16, bars, n_s0, n_s1, n_sub, ls);
-      if (j0 + 5 < n_sub) fwd3_mma_step<kBF16, 5>(j0 + 5, sb16, bars, n_s0, n_s1, n_sub, ls);
-    }
-  } else {
-    // ============================================================ softmax warps
-    const int w = warp >> 2;
-    const int t = threadIdx.x & 127;
-    const int r0 = row0 + w * kBlockM;
-    const int n = w == 0 ? n_s0 : n_s1;
-    if (r0 < p.Sq) {
-      const int row = r0 + t;
-      const bool valid_row = row < p.Sq;
-      const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-      const uint32_t tQ = lane_base + w * 64;
-      const uint32_t tS = lane_base + 128 + w * 64;
-      const uint32_t tO = lane_base + 256 + w * 128;
-      const float scale_log2 = p.scale_log2;
-      const int limit = p.causal ? min(row + p.causal_off, p.Sk - 1) : p.Sk - 1;
-      const int tile_min_limit = p.causal ? min(r0 + p.causal_off, p.Sk - 1) : p.Sk - 1;
-
-      // ---- stage this thread's Q row (128 x 16 bit = 64 packed columns) into TMEM
-      {
-        const uint4* src = reinterpret_cast<const uint4*>(p.q + (int64_t)b * p.q_sb + (int64_t)row * p.q_ss +
-                                                          (int64_t)h * p.q_sh);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint4 x = valid_row ? __ldg(src + c * 8 + i) : make_uint4(0u, 0u, 0u, 0u);
-            v[i * 4 + 0] = x.x, v[i * 4 + 1] = x.y, v[i * 4 + 2] = x.z, v[i * 4 + 3] = x.w;
-          }
-          tmem_st_x32(tQ + c * 32, v);
-        }
-      }
-      float m = -INFINITY, l = 0.f;
-      if (p.load_state) {
-        float lse_prev = -INFINITY;
-        if (valid_row) lse_prev = p.lse[(int64_t)b * p.lse_sb + (int64_t)h * p.lse_sh + row];
-        if (lse_prev != -INFINITY) {
-          m = lse_prev * kLog2e;
-          l = 1.f;
-        }
-        const float* src = p.o_acc + (int64_t)b * p.oacc_sb + (int64_t)row * p.oacc_ss + (int64_t)h * p.oacc_sh;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 f = valid_row ? __ldg(reinterpret_cast<const float4*>(src + c * 32 + i * 4))
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[i * 4 + 0] = __float_as_uint(f.x);
-            v[i * 4 + 1] = __float_as_uint(f.y);
-            v[i * 4 + 2] = __float_as_uint(f.z);
-            v[i * 4 + 3] = __float_as_uint(f.w);
-          }
-          tmem_st_x32(tO + c * 32, v);
-        }
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->q_ready[w]);
-
-      for (int j = 0; j < n; ++j) {
-        mbar_wait(&bars->s_full[w], j & 1);
-        tc_fence_after();
-        uint32_t sr[kSub];
-        tmem_ld_x32(tS, sr);
-        tmem_ld_x32(tS + 32, sr + 32);
-        tmem_wait_ld();
-        float* s = reinterpret_cast<float*>(sr);
-        const int kbase = j * kSub;
-        if (kbase + kSub - 1 > tile_min_limit) {
-#pragma unroll
-          for (int c = 0; c < kSub; ++c)
-            if (kbase + c > limit) s[c] = -INFINITY;
-        }
-        float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
-#pragma unroll
-        for (int c = 4; c < kSub; c += 4) {
-          mx0 = fmaxf(mx0, s[c]);
-          mx1 = fmaxf(mx1, s[c + 1]);
-          mx2 = fmaxf(mx2, s[c + 2]);
-          mx3 = fmaxf(mx3, s[c + 3]);
-        }
-        const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2);
-        const bool grow = m_new > m + kRescaleThreshold;
-        if (__any_sync(0xffffffffu, grow)) {
-          // S_w(j) was issued behind PV_w(j-1), so its arrival already implies O_w is up to date
-          const bool o_live = (j > 0) || p.load_state;
-          if (o_live) {
-            const float f = (m == -INFINITY) ? 0.f : ex2(m - m_new);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t v[32];
-              tmem_ld_x32(tO + c * 32, v);
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-              tmem_st_x32(tO + c * 32, v);
-            }
-            l *= f;
-          }
-          m = m_new;
-        }
-        const float neg_m = (m == -INFINITY) ? 0.f : -m;
-        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-        uint32_t pk[kSub / 2];
-#pragma unroll
-        for (int c = 0; c < kSub; c += 4) {
-          const float p0 = ex2(fmaf(s[c], scale_log2, neg_m));
-          const float p1 = ex2(fmaf(s[c + 1], scale_log2, neg_m));
-          const float p2 = ex2(fmaf(s[c + 2], scale_log2, neg_m));
-          const float p3 = ex2(fmaf(s[c + 3], scale_log2, neg_m));
-          sum0 += p0;
-          sum1 += p1;
-          sum2 += p2;
-          sum3 += p3;
-          pk[c / 2] = pack2<kBF16>(p0, p1);
-          pk[c / 2 + 1] = pack2<kBF16>(p2, p3);
-        }
-        l += (sum0 + sum1) + (sum2 + sum3);
-        tmem_st_x32(tS, pk);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->p_ready[w]);
-      }
-
-      if (n > 0) {
-        mbar_wait(&bars->o_final[w], 0);
-        tc_fence_after();
-      }
-      const bool o_live = (n > 0) || p.load_state;
-      const float inv_l = l > 0.f ? 1.f / l : 0.f;
-      const float lse_out = l > 0.f ? (m + lg2(l)) * kLn2 : -INFINITY;
-      if (valid_row) p.lse[(int64_t)b * p.lse_sb + (int64_t)h * p.lse_sh + row] = lse_out;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        if (o_live) {
-          tmem_ld_x32(tO + c * 32, v);
-          tmem_wait_ld();
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0u;
-        }
-        if (valid_row) {
-          if (p.store_lowp) {
-            uint16_t* dst = reinterpret_cast<uint16_t*>(p.o_out) + (int64_t)b * p.oout_sb +
-                            (int64_t)row * p.oout_ss + (int64_t)h * p.oout_sh + c * 32;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 o;
-              o.x = pack2<kBF16>(__uint_as_float(v[i * 8 + 0]) * inv_l, __uint_as_float(v[i * 8 + 1]) * inv_l);
-              o.y = pack2<kBF16>(__uint_as_float(v[i * 8 + 2]) * inv_l, __uint_as_float(v[i * 8 + 3]) * inv_l);
-              o.z = pack2<kBF16>(__uint_as_float(v[i * 8 + 4]) * inv_l, __uint_as_float(v[i * 8 + 5]) * inv_l);
-              o.w = pack2<kBF16>(__uint_as_float(v[i * 8 + 6]) * inv_l, __uint_as_float(v[i * 8 + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(dst + i * 8) = o;
-            }
-          } else {
-            float* dst = p.o_acc + (int64_t)b * p.oacc_sb + (int64_t)row * p.oacc_ss + (int64_t)h * p.oacc_sh +
-                         c * 32;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 o;
-              o.x = __uint_as_float(v[i * 4 + 0]) * inv_l;
-              o.y = __uint_as_float(v[i * 4 + 1]) * inv_l;
-              o.z = __uint_as_float(v[i * 4 + 2]) * inv_l;
-              o.w = __uint_as_float(v[i * 4 + 3]) * inv_l;
-              *reinterpret_cast<float4*>(dst + i * 4) = o;
-            }
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 8) tmem_dealloc(0, 512);
-}
-
-template <bool kBF16>
-static int launch_fwd3(const CUtensorMap& tmK, const CUtensorMap& tmV, const FwdParams& p, cudaStream_t stream) {
-  auto kern = fwd3_chunk_kernel<kBF16>;
-  BA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3SmemBytes));
-  dim3 grid((p.Sq + 2 * kBlockM - 1) / (2 * kBlockM), p.H, p.B);
-  kern<<<grid, kFwdThreads, kFwd3SmemBytes, stream>>>(tmK, tmV, p);
-  BA_CHECK_CUDA(cudaGetLastError());
-  return BA_OK;
-}
-
-
-// =====================================================================================================
-// v4: 128-key S tiles (QK^T as N=128 MMAs: 8 KiB of smem operands per 64 tensor cycles instead of the
-// 6 KiB per 32 cycles of the 64-key sub-tiles -- the smem operand fetch, ~64-80 B/clk, is what bounds
-// the SS-form MMAs), S single-buffered per Q tile, but P released to the MMA warp in two 64-key halves so
-// that P_a V runs while the softmax warps are still exponentiating the second half.
-// TMEM: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P (16-bit) = cols [0,32) / [32,64) of S_w.
-// =====================================================================================================
-struct __align__(8) Fwd4Barriers {
-  uint64_t q_full;
-  uint64_t k_full[2], k_empty[2];
-  uint64_t v_full[2], v_empty[2];
-  uint64_t s_full[2];      // MMA -> softmax: S_w (128 keys) ready
-  uint64_t p_ready[2][2];  // softmax -> MMA: [w][half] P half written (half 0 also: O_w rescaled)
-  uint64_t o_final[2];     // MMA -> softmax: last PV of this CTA completed
-  uint32_t tmem_base;
-};
-
-// number of 128-key tiles a 128-row Q tile starting at r0 must visit
-__device__ __forceinline__ int fwd4_trip_count(int r0, const FwdParams& p) {
-  if (r0 >= p.Sq) return 0;
-  int r_last = min(r0 + kBlockM - 1, p.Sq - 1);
-  int max_limit = p.causal ? min(r_last + p.causal_off, p.Sk - 1) : p.Sk - 1;
-  return max_limit < 0 ? 0 : max_limit / kBlockN + 1;
-}
-
-template <bool kBF16, int ST, int W>
-__device__ __forceinline__ void fwd4_issue_qk(uint32_t sb16) {  // S_w = Q_w K[ST]^T, N = 128
-  constexpr uint32_t idesc = make_idesc(kBF16, kBlockM, kBlockN, false, false), hi = desc_hi(1024);
-  const uint32_t a_lo = sb16 + ((kOffQ + W * kTileBytes) >> 4) + desc_lo_lbo(16);
-  const uint32_t k_lo = sb16 + ((kOffK + ST * kTileBytes) >> 4) + desc_lo_lbo(16);
-#pragma unroll
-  for (int kk = 0; kk < kHeadDim / 16; ++kk) {
-    const uint32_t off = ((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4;
-    umma_ss_lh(W * 128, a_lo + off, hi, k_lo + off, hi, idesc, kk > 0 ? 1u : 0u);
-  }
-}
-template <bool kBF16, int ST, int W, int HALF>
-__device__ __forceinline__ void fwd4_issue_pv(uint32_t sb16, uint32_t acc) {  // O_w += P_w[half] V[ST][half]
-  constexpr uint32_t idesc = make_idesc(kBF16, kBlockM, kHeadDim, false, true), hi = desc_hi(1024);
-  const uint32_t v_lo = sb16 + ((kOffV + ST * kTileBytes + HALF * 64 * 128) >> 4) + desc_lo_lbo(kBoxBytes);
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk)
-    umma_ts_lh(256 + W * 128, W * 128 + HALF * 32 + kk * 8, v_lo + kk * (16 * 128 / 16), hi, idesc,
-               (HALF == 1 || kk > 0) ? 1u : acc);
-}
-
-template <bool kBF16, int ST>
-__device__ __forceinline__ void fwd4_mma_tile(int i, uint32_t sb16, Fwd4Barriers* bars, int n_t0, int n_t1, int n_max,
-                                              bool load_state) {
-  constexpr int STN = ST ^ 1;
-  mbar_wait(&bars->v_full[ST], (i >> 1) & 1);
-  tc_fence_after();
-  const bool next = (i + 1) < n_max;
-  if (next) {
-    mbar_wait(&bars->k_full[STN], ((i + 1) >> 1) & 1);
-    tc_fence_after();
-  }
-  const uint32_t acc = (i > 0 || load_state) ? 1u : 0u;
-  if (i < n_t0) {
-    mbar_wait(&bars->p_ready[0][0], i & 1);
-    tc_fence_after();
-    fwd4_issue_pv<kBF16, ST, 0, 0>(sb16, acc);
-    mbar_wait(&bars->p_ready[0][1], i & 1);
-    tc_fence_after();
-    fwd4_issue_pv<kBF16, ST, 0, 1>(sb16, 1u);
-    if (i == n_t0 - 1) umma_commit(&bars->o_final[0]);
-  }
-  if (i + 1 < n_t0) {
-    fwd4_issue_qk<kBF16, STN, 0>(sb16);
-    umma_commit(&bars->s_full[0]);
-  }
-  if (i < n_t1) {
-    mbar_wait(&bars->p_ready[1][0], i & 1);
-    tc_fence_after();
-    fwd4_issue_pv<kBF16, ST, 1, 0>(sb16, acc);
-    mbar_wait(&bars->p_ready[1][1], i & 1);
-    tc_fence_after();
-    fwd4_issue_pv<kBF16, ST, 1, 1>(sb16, 1u);
-    if (i == n_t1 - 1) umma_commit(&bars->o_final[1]);
-  }
-  umma_commit(&bars->v_empty[ST]);
-  if (i + 1 < n_t1) {
-    fwd4_issue_qk<kBF16, STN, 1>(sb16);
-    umma_commit(&bars->s_full[1]);
-  }
-  if (next) umma_commit(&bars->k_empty[STN]);
-}
-
-template <bool kBF16>
-__global__ void __launch_bounds__(kFwdThreads, 1)
-fwd4_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                  const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw;
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* sQ = smem + kOffQ;
-  uint8_t* sK = smem + kOffK;
-  uint8_t* sV = smem + kOffV;
-  Fwd4Barriers* bars = reinterpret_cast<Fwd4Barriers*>(smem + kOffBars);
-
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-  const int lane = threadIdx.x & 31;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int row0 = (p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * (2 * kBlockM);
-  const int n_t0 = fwd4_trip_count(row0, p);
-  const int n_t1 = fwd4_trip_count(row0 + kBlockM, p);
-  const int n_max = max(n_t0, n_t1);
-
-  if (warp == 9 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-  }
-  if (warp == 8) {
-    if (lane == 0) {
-      mbar_init(&bars->q_full, 1);
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&bars->k_full[i], 1);
-        mbar_init(&bars->k_empty[i], 1);
-        mbar_init(&bars->v_full[i], 1);
-        mbar_init(&bars->v_empty[i], 1);
-        mbar_init(&bars->s_full[i], 1);
-        mbar_init(&bars->p_ready[i][0], 4);
-        mbar_init(&bars->p_ready[i][1], 4);
-        mbar_init(&bars->o_final[i], 1);
-      }
-      fence_mbar_init();
-    }
-    __syncwarp();
-    tmem_alloc(&bars->tmem_base, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (bars->tmem_base != 0) __trap();
-
-  if (warp == 9) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&bars->q_full, 2 * kTileBytes);
-      for (int w = 0; w < 2; ++w)
-        for (int half = 0; half < 2; ++half)
-          tma_load_4d(sQ + w * kTileBytes + half * kBoxBytes, &tmQ, &bars->q_full, half * 64, h, row0 + w * kBlockM, b);
-      for (int i = 0; i < n_max; ++i) {
-        const int st = i & 1, ph = (i >> 1) & 1;
-        mbar_wait(&bars->k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&bars->k_full[st], kTileBytes);
-        for (int half = 0; half < 2; ++half)
-          tma_load_4d(sK + st * kTileBytes + half * kBoxBytes, &tmK, &bars->k_full[st], half * 64, h, i * kBlockN, b);
-        mbar_wait(&bars->v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&bars->v_full[st], kTileBytes);
-        for (int half = 0; half < 2; ++half)
-          tma_load_4d(sV + st * kTileBytes + half * kBoxBytes, &tmV, &bars->v_full[st], half * 64, h, i * kBlockN, b);
-      }
-    }
-  } else if (warp == 8) {
-    const uint32_t sb16 = smem_u32(smem) >> 4;
-    if (n_max > 0) {
-      mbar_wait(&bars->q_full, 0);
-      mbar_wait(&bars->k_full[0], 0);
-      tc_fence_after();
-      if (n_t0 > 0) {
-        fwd4_issue_qk<kBF16, 0, 0>(sb16);
-        umma_commit(&bars->s_full[0]);
-      }
-      if (n_t1 > 0) {
-        fwd4_issue_qk<kBF16, 0, 1>(sb16);
-        umma_commit(&bars->s_full[1]);
-      }
-      umma_commit(&bars->k_empty[0]);
-    }
-    const bool ls = p.load_state != 0;
-    for (int i0 = 0; i0 < n_max; i0 += 2) {
-      fwd4_mma_tile<kBF16, 0>(i0, sb16, bars, n_t0, n_t1, n_max, ls);
-      if (i0 + 1 < n_max) fwd4_mma_tile<kBF16, 1>(i0 + 1, sb16, bars, n_t0, n_t1, n_max, ls);
-    }
-  } else {
-    const int w = warp >> 2;
-    const int t = threadIdx.x & 127;
-    const int r0 = row0 + w * kBlockM;
-    const int n = w == 0 ? n_t0 : n_t1;
-    if (r0 < p.Sq) {
-      const int row = r0 + t;
-      const bool valid_row = row < p.Sq;
-      const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-      const uint32_t tS = lane_base + w * 128;
-      const uint32_t tO = lane_base + 256 + w * 128;
-      const float scale_log2 = p.scale_log2;
-      const int limit = p.causal ? min(row + p.causal_off, p.Sk - 1) : p.Sk - 1;
-      const int tile_min_limit = p.causal ? min(r0 + p.causal_off, p.Sk - 1) : p.Sk - 1;
-
-      float m = -INFINITY, l = 0.f;
-      if (p.load_state) {
-        float lse_prev = -INFINITY;
-        if (valid_row) lse_prev = p.lse[(int64_t)b * p.lse_sb + (int64_t)h * p.lse_sh + row];
-        if (lse_prev != -INFINITY) {
-          m = lse_prev * kLog2e;
-          l = 1.f;
-        }
-        const float* src = p.o_acc + (int64_t)b * p.oacc_sb + (int64_t)row * p.oacc_ss + (int64_t)h * p.oacc_sh;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 f = valid_row ? __ldg(reinterpret_cast<const float4*>(src + c * 32 + j * 4))
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[j * 4 + 0] = __float_as_uint(f.x);
-            v[j * 4 + 1] = __float_as_uint(f.y);
-            v[j * 4 + 2] = __float_as_uint(f.z);
-            v[j * 4 + 3] = __float_as_uint(f.w);
-          }
-          tmem_st_x32(tO + c * 32, v);
-        }
-        tmem_wait_st();
-      }
-
-      for (int i = 0; i < n; ++i) {
-        mbar_wait(&bars->s_full[w], i & 1);
-        tc_fence_after();
-        uint32_t sr[128];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, sr + c * 32);
-        tmem_wait_ld();
-        float* s = reinterpret_cast<float*>(sr);
-        const int kbase = i * kBlockN;
-        if (kbase + kBlockN - 1 > tile_min_limit) {
-#pragma unroll
-          for (int c = 0; c < 128; ++c)
-            if (kbase + c > limit) s[c] = -INFINITY;
-        }
-        float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
-#pragma unroll
-        for (int c = 4; c < 128; c += 4) {
-          mx0 = fmaxf(mx0, s[c]);
-          mx1 = fmaxf(mx1, s[c + 1]);
-          mx2 = fmaxf(mx2, s[c + 2]);
-          mx3 = fmaxf(mx3, s[c + 3]);
-        }
-        const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2);
-        const bool grow = m_new > m + kRescaleThreshold;
-        if (__any_sync(0xffffffffu, grow)) {
-          // S_w(i) was issued behind both PV halves of tile i-1: its arrival implies O_w is up to date
-          const bool o_live = (i > 0) || p.load_state;
-          if (o_live) {
-            const float f = (m == -INFINITY) ? 0.f : ex2(m - m_new);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t v[32];
-              tmem_ld_x32(tO + c * 32, v);
-              tmem_wait_ld();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * f);
-              tmem_st_x32(tO + c * 32, v);
-            }
-            l *= f;
-          }
-          m = m_new;
-        }
-        const float neg_m = (m == -INFINITY) ? 0.f : -m;
-        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t pk[32];
-#pragma unroll
-          for (int c = 0; c < 64; c += 4) {
-            const int cc = half * 64 + c;
-            const float p0 = ex2(fmaf(s[cc], scale_log2, neg_m));
-            const float p1 = ex2(fmaf(s[cc + 1], scale_log2, neg_m));
-            const float p2 = ex2(fmaf(s[cc + 2], scale_log2, neg_m));
-            const float p3 = ex2(fmaf(s[cc + 3], scale_log2, neg_m));
-            sum0 += p0;
-            sum1 += p1;
-            sum2 += p2;
-            sum3 += p3;
-            pk[c / 2] = pack2<kBF16>(p0, p1);
-            pk[c / 2 + 1] = pack2<kBF16>(p2, p3);
-          }
-          tmem_st_x32(tS + half * 32, pk);
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->p_ready[w][half]);
-        }
-        l += (sum0 + sum1) + (sum2 + sum3);
-      }
-
-      if (n > 0) {
-        mbar_wait(&bars->o_final[w], 0);
-        tc_fence_after();
-      }
-      const bool o_live = (n > 0) || p.load_state;
-      const float inv_l = l > 0.f ? 1.f / l : 0.f;
-      const float lse_out = l > 0.f ? (m + lg2(l)) * kLn2 : -INFINITY;
-      if (valid_row) p.lse[(int64_t)b * p.lse_sb + (int64_t)h * p.lse_sh + row] = lse_out;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        if (o_live) {
-          tmem_ld_x32(tO + c * 32, v);
-          tmem_wait_ld();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0u;
-        }
-        if (valid_row) {
-          if (p.store_lowp) {
-            uint16_t* dst = reinterpret_cast<uint16_t*>(p.o_out) + (int64_t)b * p.oout_sb +
-                            (int64_t)row * p.oout_ss + (int64_t)h * p.oout_sh + c * 32;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack2<kBF16>(__uint_as_float(v[j * 8 + 0]) * inv_l, __uint_as_float(v[j * 8 + 1]) * inv_l);
-              o.y = pack2<kBF16>(__uint_as_float(v[j * 8 + 2]) * inv_l, __uint_as_float(v[j * 8 + 3]) * inv_l);
-              o.z = pack2<kBF16>(__uint_as_float(v[j * 8 + 4]) * inv_l, __uint_as_float(v[j * 8 + 5]) * inv_l);
-              o.w = pack2<kBF16>(__uint_as_float(v[j * 8 + 6]) * inv_l, __uint_as_float(v[j * 8 + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(dst + j * 8) = o;
-            }
-          } else {
-            float* dst = p.o_acc + (int64_t)b * p.oacc_sb + (int64_t)row * p.oacc_ss + (int64_t)h * p.oacc_sh +
-                         c * 32;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 o;
-              o.x = __uint_as_float(v[j * 4 + 0]) * inv_l;
-              o.y = __uint_as_float(v[j * 4 + 1]) * inv_l;
-              o.z = __uint_as_float(v[j * 4 + 2]) * inv_l;
-              o.w = __uint_as_float(v[j * 4 + 3]) * inv_l;
-              *reinterpret_cast<float4*>(dst + j * 4) = o;
-            }
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 8) tmem_dealloc(0, 512);
-}
-
-template <bool kBF16>
-static int launch_fwd4(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const FwdParams& p,
-                       cudaStream_t stream) {
-  auto kern = fwd4_chunk_kernel<kBF16>;
-  BA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
-  dim3 grid((p.Sq + 2 * kBlockM - 1) / (2 * kBlockM), p.H, p.B);
-  kern<<<grid, kFwdThreads, kFwdSmemBytes, stream>>>(tmQ, tmK, tmV, p);
-  BA_CHECK_CUDA(cudaGetLastError());
-  return BA_OK;
-}
-
 template <bool kBF16, int kPoly>
 static int launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const FwdParams& p,
                       cudaStream_t stream) {
@@ -1172,8 +447,6 @@ extern "C" int ba_fwd_chunk(ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_tensor4
   if ((rc = make_tensor_map(&tmV, v, B, Sk, H, D, dt, 2, 64, kBlockN, true))) return rc;
 
   FwdParams p;
-  p.q = static_cast<const uint16_t*>(q.ptr);
-  p.q_sb = q.stride_b, p.q_ss = q.stride_s, p.q_sh = q.stride_h;
   p.o_acc = static_cast<float*>(o_acc.ptr);
   p.oacc_sb = o_acc.stride_b, p.oacc_ss = o_acc.stride_s, p.oacc_sh = o_acc.stride_h;
   p.lse = lse.ptr;
@@ -1187,29 +460,6 @@ extern "C" int ba_fwd_chunk(ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_tensor4
   p.load_state = first ? 0 : 1;
   p.store_lowp = last ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static const int impl = [] {
-    const char* e = getenv("BA_FWD_IMPL");
-    return e ? atoi(e) : 2;
-  }();
-  if (impl == 6) {
-    CUtensorMap tmK64;
-    if ((rc = make_tensor_map(&tmK64, k, B, Sk, H, D, dt, 2, 64, 64, true))) return rc;
-    return launch_fwd_pair6(dtype, tmQ, tmK64, tmV, p, st);
-  }
-  if (impl == 5) {
-    BA_REQUIRE((reinterpret_cast<uintptr_t>(q.ptr) & 15) == 0 && q.stride_b % 8 == 0 && q.stride_s % 8 == 0 &&
-                   q.stride_h % 8 == 0, "ba_fwd_chunk: q must be a 16-byte aligned view");
-    CUtensorMap tmK64;
-    if ((rc = make_tensor_map(&tmK64, k, B, Sk, H, D, dt, 2, 64, 64, true))) return rc;
-    return launch_fwd_pair(dtype, tmK64, tmV, p, st);
-  }
-  if (impl == 4)
-    return dtype == BA_DTYPE_BF16 ? launch_fwd4<true>(tmQ, tmK, tmV, p, st) : launch_fwd4<false>(tmQ, tmK, tmV, p, st);
-  if (impl == 3) {
-    BA_REQUIRE((reinterpret_cast<uintptr_t>(q.ptr) & 15) == 0 && q.stride_b % 8 == 0 && q.stride_s % 8 == 0 &&
-                   q.stride_h % 8 == 0, "ba_fwd_chunk: q must be a 16-byte aligned view");
-    return dtype == BA_DTYPE_BF16 ? launch_fwd3<true>(tmK, tmV, p, st) : launch_fwd3<false>(tmK, tmV, p, st);
-  }
   // BA_FWD_POLY (tuning knob, read once): 0 = all exponentials on MUFU, 4 = every 4th, 8 = every 8th on FMA
   static const int poly = [] {
     const char* e = getenv("BA_FWD_POLY");

@@ -77,8 +77,11 @@ int make_tensor_map(CUtensorMap* out, const ba_tensor4& t, int B, int S, int H, 
 
 }  // namespace ba
 
+#ifdef BA_SELFTEST_LIB
+extern "C" const char* ba_selftest_last_error(void) { return ba::g_err; }
+#else
 extern "C" const char* ba_last_error(void) { return ba::g_err; }
-extern "C" int ba_version(void) { return 100; }
+extern "C" int ba_version(void) { return 200; }
 extern "C" int ba_device_check(void) {
   int dev = 0;
   BA_CHECK_CUDA(cudaGetDevice(&dev));
@@ -91,3 +94,4 @@ extern "C" int ba_device_check(void) {
   }
   return BA_OK;
 }
+#endif

@@ -3,6 +3,7 @@
 // swizzle layout, the K-major and MN-major shared-memory descriptors, the
 // instruction descriptor, the TMEM load/store lane mapping and the TS-form MMA,
 // so a failing attention parity test can be traced to one assumption.
+#include "burst_attn_b200_selftest.h"
 #include "host_common.h"
 #include "sm100_ptx.cuh"
 

@@ -3,6 +3,7 @@
 // (SS / TS, N = 64 / 128 / 256, cta_group 1 / 2), tcgen05.ld / st throughput and whether TMEM reads slow a
 // concurrent MMA chain, MUFU ex2 throughput, commit -> mbarrier and cluster-remote arrive latencies.
 // Operand CONTENTS are whatever shared memory / TMEM hold (timing only); every address is in bounds.
+#include "burst_attn_b200_selftest.h"
 #include "host_common.h"
 #include "sm100_ptx.cuh"
 

@@ -18,9 +18,9 @@ def selftest(mode, a, b, out_dtype=torch.float32):
         out = torch.zeros(8192, device=a.device, dtype=torch.int16)
     else:
         out = torch.zeros(a.shape[0], 128, device=a.device, dtype=torch.float32)  # modes 4/5: a is [256,128]
-    rc = nat.lib().ba_selftest(mode, a.data_ptr(), b.data_ptr(), out.data_ptr(), nat.dtype_code(a.dtype),
+    rc = nat.selftest_lib().ba_selftest(mode, a.data_ptr(), b.data_ptr(), out.data_ptr(), nat.dtype_code(a.dtype),
                                nat.stream_ptr(a.device))
-    nat.check(rc, "ba_selftest")
+    nat.check_selftest(rc, "ba_selftest")
     torch.cuda.synchronize()
     return out
 

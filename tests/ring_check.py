@@ -44,6 +44,8 @@ def run_cases(rank, world, dev):
     # had a multi-GPU session.
     intra = int(os.environ.get("RING_CHECK_DOUBLE", "0"))
     double_group = _double_group(world, intra) if intra and world % intra == 0 and 1 < intra < world else None
+    if double_group is not None:
+        os.environ["BA_DOUBLE_RING"] = "1"
     for dg in ([None, None], double_group):
         if dg is None:
             continue

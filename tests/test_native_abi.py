@@ -35,6 +35,19 @@ def test_library_exports_every_declared_symbol(nat):
         assert hasattr(L, name), name
 
 
+def test_selftest_library_is_separate_from_the_product(nat):
+    """Diagnostics (ba_selftest, ba_ubench) live in their own header and library, not in the drop-in boundary."""
+    hdr = open(os.path.join(ROOT, "include", "burst_attn_b200_selftest.h")).read()
+    declared = sorted(set(re.findall(r"\b(ba_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(nat._SELFTEST_EXPORTS)
+    T = ctypes.CDLL(nat.SELFTEST_LIB_PATH)
+    for name in declared:
+        assert hasattr(T, name), name
+    L = ctypes.CDLL(nat.LIB_PATH)
+    for name in ("ba_selftest", "ba_ubench"):
+        assert not hasattr(L, name), f"{name} must not be exported by the product library"
+
+
 def test_bad_arguments_return_error_string(nat):
     L = nat.lib()
     z4 = nat.ba_tensor4(None, 0, 0, 0)
@@ -49,7 +62,7 @@ def test_bad_arguments_return_error_string(nat):
     assert rc != 0 and b"ba_ring_arena_create" in L.ba_last_error()
     rc = L.ba_ring_arena_connect(None, None, None)
     assert rc != 0 and b"ba_ring_arena_connect" in L.ba_last_error()
-    assert L.ba_version() >= 100
+    assert L.ba_version() >= 200
 
 
 def test_missing_library_fails_loudly(nat, monkeypatch):

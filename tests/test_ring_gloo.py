@@ -108,6 +108,7 @@ def _worker(rank, world, port, case, seq_dim, errq, intra=0, dq_groups=False):
             return  # reference asserts causal needs flash == "cuda"
         double_group = [None, None]
         if intra:  # hierarchical ring: nodes of `intra` consecutive ranks (reference test/test_burst.py:120-156)
+            os.environ["BA_DOUBLE_RING"] = "1"  # opt-in (flat ring over process_group is the default)
             rows = [list(range(n * intra, (n + 1) * intra)) for n in range(world // intra)]
             cols = [list(c) for c in zip(*rows)]
             mk = lambda ranks: dist.new_subgroups_by_enumeration(ranks, backend="gloo")[0]  # noqa: E731

@@ -16,7 +16,7 @@ from burst_attn import native as nat  # noqa: E402
 
 def selftest(mode, a, b):
     out = torch.zeros(256, 128, device=a.device, dtype=torch.float32)
-    nat.check(nat.lib().ba_selftest(mode, a.data_ptr(), b.data_ptr(), out.data_ptr(), nat.dtype_code(a.dtype),
+    nat.check_selftest(nat.selftest_lib().ba_selftest(mode, a.data_ptr(), b.data_ptr(), out.data_ptr(), nat.dtype_code(a.dtype),
                                     nat.stream_ptr(a.device)), f"ba_selftest({mode})")
     torch.cuda.synchronize()
     return out

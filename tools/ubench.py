@@ -24,7 +24,7 @@ MMA = {  # mode: (label, M per SM, N, smem operand bytes per SM per dispatch)
 
 def run(lib, mode, iters, grid):
     out = (ctypes.c_int64 * 4)()
-    native.check(lib.ba_ubench(mode, iters, grid, out, native.stream_ptr()), f"ba_ubench({mode})")
+    native.check_selftest(lib.ba_ubench(mode, iters, grid, out, native.stream_ptr()), f"ba_ubench({mode})")
     return list(out)
 
 
@@ -37,8 +37,8 @@ def main():
                          "poisons the CUDA context)")
     a = ap.parse_args()
     torch.cuda.init()
-    lib = native.lib()
-    native.check(lib.ba_device_check(), "ba_device_check")
+    lib = native.selftest_lib()
+    native.check(native.lib().ba_device_check(), "ba_device_check")
     print(f"# ubench grid={a.grid} iters={a.iters} (cycles are per SM, max over CTAs)")
     lat = run(lib, 12, 1, 1)[0]
     print(f"single MMA issue -> commit -> mbarrier wait: {lat} clk")
