@@ -530,11 +530,25 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
             for h, t in zip(ho[1:], grads):
                 h.copy_(t, non_blocking=True)
             cur.wait_stream(copy_s)
+        def e2e_step_host():
+            # one rank: hand the pinned HOST tensors to the public API; its L2-blocked drivers stream K/V blocks and dO
+            # up and O / dQ / dK / dV blocks down under the kernels (burst_attn/host_stream.py)
+            qq, kk, vv = (h.detach().requires_grad_() for h in (hq, hk, hv))
+            o = burst_attn_func(qq, kk, vv, None, "cuda", args.causal, True, False, None, args.double_group)
+            return (o,) + tuple(torch.autograd.grad(o, (qq, kk, vv), hdo))
+
+        if world == 1:
+            e2e_step = e2e_step_host  # noqa: F811
+        e2e_step()
         e2e_step()
         ms_e2e = timed(e2e_step, K)
         nbytes = hq.numel() * hq.element_size()
         e2e = {"value": fl_step / (ms_e2e * 1e-3) / 1e12, "unit": "TFLOPS/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": 4 * nbytes * world, "d2h_bytes_per_step": 4 * nbytes * world}
+               "h2d_bytes_per_step": 4 * nbytes * world, "d2h_bytes_per_step": 4 * nbytes * world,
+               "how": ("burst_attn_func on pinned host tensors (host-resident operands: copies stream under the "
+                       "L2-blocked sub-launches)" if world == 1 else
+                       "pinned host buffers -> device tensors -> burst_attn_func; dO up under the forward, O down under "
+                       "the backward on a copy stream")}
 
     # ---- A/B: the same step with the ring replaced by a local buffer swap -> exposed ring-communication time
     ab = None

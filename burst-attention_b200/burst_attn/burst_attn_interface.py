@@ -505,6 +505,19 @@ def _unpad(t, D):
 
 
 def _op_forward(ctx, q, k, v, mode):
+    ctx.host = False
+    if q.device.type == "cpu":
+        # host-resident operands (pinned CPU tensors, one rank): copies stream under the kernels (host_stream.py)
+        from . import host_stream
+        if not host_stream.is_host_call(q, k, v):
+            raise TypeError("burst_attn_b200 needs CUDA tensors (or pinned CPU tensors on a CUDA machine); there is "
+                            "no CPU implementation")
+        assert ctx.topo.W == 1, "host-resident operands are supported on a single rank only (pass device tensors)"
+        assert q.shape[-1] == getattr(get_ops(), "tile_head_dim", q.shape[-1]), "host-resident operands need head_dim 128"
+        ctx.host, ctx.mode, ctx.head_dim = True, mode, q.shape[-1]
+        o_host, saved = host_stream.forward(q, k, v, ctx.softmax_scale, ctx.seq_dim, mode != "none", _l2_block())
+        ctx.save_for_backward(*saved)
+        return o_host
     (qp, kp, vp), ctx.head_dim = _pad_head_dim(get_ops(), [q, k, v])
     out, lse = _ring_forward(qp, kp, vp, ctx.softmax_scale, ctx.seq_dim, mode, ctx.topo)
     ctx.mode = mode
@@ -513,6 +526,11 @@ def _op_forward(ctx, q, k, v, mode):
 
 
 def _op_backward(ctx, grad_output):
+    if ctx.host:
+        from . import host_stream
+        grads = host_stream.backward(grad_output, ctx.saved_tensors, ctx.softmax_scale, ctx.seq_dim,
+                                     ctx.mode != "none", _l2_block(), ctx.deterministic)
+        return tuple(grads) + (None,) * 7
     q, k, v, lse, out = ctx.saved_tensors
     (g,), _ = _pad_head_dim(get_ops(), [grad_output])
     dq, dk, dv = _ring_backward(g, q, k, v, out, lse, ctx.softmax_scale, ctx.seq_dim, ctx.mode, ctx.topo,

@@ -19,6 +19,7 @@
 // TMEM (512 cols): S^T/P^T [0,128)  dP^T/dQ [128,256)  dK [256,384)  dV [384,512).
 // smem: K 32K, V 32K, Q 2x32K, dO 32K, dS 32K, dQ staging 2x16K, row stats 2x1K.
 #include <math.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <vector>
@@ -44,6 +45,44 @@ __device__ __forceinline__ void reg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
+// ---- row statistics folded into the GEMMs ("fold") --------------------------------------------------------
+// P^T = exp2(S^T c - lse2[q]) and dS^T = P^T o (dP^T - delta[q]) need a per-COLUMN value in a thread = key-row
+// layout; reading them from shared memory costs 512 broadcast-LDS wavefronts per Q block on the shared-memory
+// data pipe this kernel is bound by (profiles/README.md).  Instead the tensor core adds them: one extra K = 16
+// step per GEMM,  S^T += 1[key] (x) (-lse/scale)[q],  dP^T += 1[key] (x) (-delta)[q],  with the fp32 value split
+// into three 16-bit parts (hi + lo + lolo: exact to fp32 round-off, products with 1.0 are exact, fp32 accumulate).
+// Operand tiles are K-major, NO swizzle (core matrix = 8 rows x 16 B, contiguous):
+//   B (per Q block, written by the loader warp): row q = [l0 l1 l2 d0 d1 d2 0 0]; 16 row groups x 128 B = 2 KiB;
+//     its second K chunk (k = 8..15) re-reads the first (LBO = 0): harmless, A is zero there;
+//   A (constant): ONE 128-byte core matrix of identical rows [1 1 1 0 0 0 0 0] (lse) or [0 0 0 1 1 1 0 0]
+//     (delta) shared by all 16 row groups (SBO = 0), second K chunk = a zero core matrix.
+BA_DEVICE uint64_t make_smem_desc_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell); swizzle field = 0: none
+  return d;
+}
+template <bool kBF16>
+BA_DEVICE uint32_t to16(float x) {
+  if constexpr (kBF16) return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+  else return __half_as_ushort(__float2half_rn(x));
+}
+template <bool kBF16>
+BA_DEVICE float from16(uint32_t h) {
+  if constexpr (kBF16) return __bfloat162float(__ushort_as_bfloat16(static_cast<unsigned short>(h)));
+  else return __half2float(__ushort_as_half(static_cast<unsigned short>(h)));
+}
+template <bool kBF16>
+BA_DEVICE void split3(float x, uint32_t& h0, uint32_t& h1, uint32_t& h2) {
+  h0 = to16<kBF16>(x);
+  float r = x - from16<kBF16>(h0);
+  h1 = to16<kBF16>(r);
+  r -= from16<kBF16>(h1);
+  h2 = to16<kBF16>(r);
+}
+
 struct BwdParams {
   const float* lse;
   int64_t lse_sb, lse_sh;
@@ -54,7 +93,7 @@ struct BwdParams {
   float* dv_acc;
   int64_t dv_sb, dv_ss, dv_sh;
   int B, Sq, Sk, H;
-  float scale, scale_log2;
+  float scale, scale_log2, inv_scale;
   int causal, causal_off;
   int* sem;     // deterministic mode: [B][H][nQ] turn counters ordering the dQ reductions by key block; else null
   int* ticket;  // deterministic mode: [B][H] key-block tickets (a CTA's key block = the order in which it STARTED)
@@ -85,12 +124,13 @@ constexpr int kOffQ = kOffV + kTileB;        // 2 stages
 constexpr int kOffDO = kOffQ + 2 * kTileB;   // 1 stage
 constexpr int kOffDS = kOffDO + kTileB;
 constexpr int kOffDQ = kOffDS + kTileB;      // 2 staging boxes
-constexpr int kOffStat = kOffDQ + 2 * kDqStageB;  // [2 stages][lse2 128 | delta 128] fp32
-constexpr int kOffBar = kOffStat + 2 * 2 * kTile * 4;
+constexpr int kOffStat = kOffDQ + 2 * kDqStageB;  // fold: [128 q rows][16 B] row-stat operand tile; else [2][lse2|delta] fp32
+constexpr int kOffFoldA = kOffStat + 2 * 2 * kTile * 4;  // fold: [ones(lse slots) 128 B][ones(delta slots) 128 B][zeros 128 B]
+constexpr int kOffBar = kOffFoldA + 512;
 constexpr int kBwdSmemBytes = kOffBar + 256;  // no align slack: the dynamic smem base is checked to be 1 KiB aligned
 static_assert(kBwdSmemBytes <= 232448, "backward kernel exceeds 227 KiB of shared memory");
 
-template <bool kBF16>
+template <bool kBF16, bool kFold>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -153,6 +193,15 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&bars->dkv_full, 1);
       fence_mbar_init();
     }
+    if (kFold && lane < 24) {  // constant A operands of the row-stat K steps: 3 core matrices of 8 x 16 B
+      constexpr uint32_t one = kBF16 ? 0x3F80u : 0x3C00u;
+      const int m = lane >> 3;  // 0: ones in the lse slots 0..2, 1: ones in the delta slots 3..5, 2: zeros
+      uint4 row = make_uint4(0u, 0u, 0u, 0u);
+      if (m == 0) row = make_uint4(one | (one << 16), one, 0u, 0u);
+      if (m == 1) row = make_uint4(0u, one << 16, one | (one << 16), 0u);
+      *reinterpret_cast<uint4*>(smem + kOffFoldA + lane * 16) = row;
+      fence_proxy_async_smem();
+    }
     __syncwarp();
     tmem_alloc(&bars->tmem_base, 512);
     tmem_relinquish();
@@ -179,28 +228,57 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int it = 0; it < n_it; ++it) {
       const int q0 = (i_begin + it) * kTile;
       const int st = it & 1;
-      mbar_wait(&bars->q_empty[st], ((it >> 1) & 1) ^ 1);
-      // row statistics of this Q block: lse in log2 units (+inf for padding rows -> P = 0), delta
-      float* stat = sStat + st * 2 * kTile;
+      // row statistics of this Q block (lane handles rows lane + 32 j): lse, delta
+      float sl[4], sd[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int r = lane + 32 * j;
-        const int row = q0 + r;
-        float l2 = INFINITY, dl = 0.f;
+        const int row = q0 + lane + 32 * j;
+        float l = INFINITY, dl = 0.f;  // +inf: padding row, or a row that saw no key at all -> P = 0
         if (row < p.Sq) {
-          l2 = __ldg(p.lse + (int64_t)b * p.lse_sb + (int64_t)h * p.lse_sh + row) * kBwdLog2e;
+          l = __ldg(p.lse + (int64_t)b * p.lse_sb + (int64_t)h * p.lse_sh + row);
           dl = __ldg(p.delta + (int64_t)b * p.dl_sb + (int64_t)h * p.dl_sh + row);
-          if (l2 == -INFINITY) l2 = INFINITY;  // a row that saw no key at all contributes nothing
+          if (l == -INFINITY) l = INFINITY;
         }
-        stat[r] = l2;
-        stat[kTile + r] = dl;
+        sl[j] = l, sd[j] = dl;
       }
-      __syncwarp();
+      mbar_wait(&bars->q_empty[st], ((it >> 1) & 1) ^ 1);  // also: the compute warps are done with stat stage st
       if (lane == 0) {
-        mbar_arrive(&bars->stat_full[st]);
         mbar_arrive_expect_tx(&bars->q_full[st], kTileB);
         for (int half = 0; half < 2; ++half)
           tma_load_4d(sQ + st * kTileB + half * kBoxB, &tmQ, &bars->q_full[st], half * 64, h, q0, b);
+      }
+      if constexpr (kFold) {
+        // ONE operand tile (lse and delta share a row): it may be overwritten once the MMAs that read it for the
+        // previous Q block -- S^T(it-1), then dP^T(it-1) -- have completed, i.e. dp_full(it-1).  dP^T(it) cannot be
+        // issued before this warp has loaded dO(it) below, so that barrier cannot run a phase ahead of us.
+        if (it > 0) mbar_wait(&bars->dp_full, (it - 1) & 1);
+        constexpr float kBig = kBF16 ? 1e30f : 60000.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = lane + 32 * j;
+          const float xl = fmaxf(-sl[j] * p.inv_scale, -kBig);  // S^T + xl = (S^T c - lse2) / c
+          const float xd = fminf(fmaxf(-sd[j], -kBig), kBig);
+          uint32_t l0, l1, l2, d0, d1, d2;
+          split3<kBF16>(xl, l0, l1, l2);
+          split3<kBF16>(xd, d0, d1, d2);
+          *reinterpret_cast<uint4*>(smem + kOffStat + (r >> 3) * 128 + (r & 7) * 16) =
+              make_uint4(l0 | (l1 << 16), l2 | (d0 << 16), d1 | (d2 << 16), 0u);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->stat_full[0]);
+      } else {
+        // lse in log2 units, delta: read by the compute warps (broadcast LDS)
+        float* stat = sStat + st * 2 * kTile;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          stat[lane + 32 * j] = sl[j] * kBwdLog2e;
+          stat[kTile + lane + 32 * j] = sd[j];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->stat_full[st]);
+      }
+      if (lane == 0) {
         mbar_wait(&bars->do_empty, (it & 1) ^ 1);
         mbar_arrive_expect_tx(&bars->do_full, kTileB);
         for (int half = 0; half < 2; ++half)
@@ -226,19 +304,31 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint64_t dDS_k = make_smem_desc(smem_u32(sDS), 16, 1024);        // dS^T [key][q] as K-major A
       const uint64_t dDS_n = make_smem_desc(smem_u32(sDS), kBoxB, 1024);     // ... as MN-major A (M = q)
 
+      // row-stat K steps (kFold): no-swizzle K-major tiles, see the comment at make_smem_desc_noswz
+      const uint32_t sFA = smem_u32(smem + kOffFoldA);
+      const uint64_t dA_lse = make_smem_desc_noswz(sFA, 256, 0);        // ones in slots 0..2 | zero chunk
+      const uint64_t dA_dl = make_smem_desc_noswz(sFA + 128, 128, 0);   // ones in slots 3..5 | zero chunk
+      const uint64_t dB_stat = make_smem_desc_noswz(smem_u32(smem + kOffStat), 0, 128);
+
       auto kstep_k = [](int kk) -> uint32_t { return (kk >> 2) * kBoxB + (kk & 3) * 32; };  // K-major k-step
       auto kstep_n = [](int kk) -> uint32_t { return kk * 16 * 128; };                      // MN-major k-step
 
-      auto issue_S = [&](int st) {  // S^T = K Q^T
+      auto issue_S = [&](int st, int it_of_block) {  // S^T = K Q^T  (kFold: ... - lse/scale)
         const uint64_t dQ_k = make_smem_desc(smem_u32(sQ + st * kTileB), 16, 1024);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           umma_ss(tS, desc_advance(dK_k, kstep_k(kk)), desc_advance(dQ_k, kstep_k(kk)), id_kk, kk > 0);
+        if constexpr (kFold) {
+          mbar_wait(&bars->stat_full[0], it_of_block & 1);
+          tc_fence_after();
+          umma_ss(tS, dA_lse, dB_stat, id_kk, 1);
+        }
       };
-      auto issue_dP = [&]() {  // dP^T = V dO^T
+      auto issue_dP = [&]() {  // dP^T = V dO^T  (kFold: ... - delta; same operand tile as the S^T just issued)
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           umma_ss(tDP, desc_advance(dV_k, kstep_k(kk)), desc_advance(dDO_k, kstep_k(kk)), id_kk, kk > 0);
+        if constexpr (kFold) umma_ss(tDP, dA_dl, dB_stat, id_kk, 1);
       };
       auto issue_dV = [&](bool acc) {  // dV += P^T dO ; P^T cols: q 0..63 at [0,32), q 64..127 at [64,96)
 #pragma unroll
@@ -265,7 +355,7 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_wait(&bars->kv_full, 0);
       mbar_wait(&bars->q_full[0], 0);
       tc_fence_after();
-      issue_S(0);
+      issue_S(0, 0);
       umma_commit(&bars->s_full);
       mbar_wait(&bars->do_full, 0);
       tc_fence_after();
@@ -281,7 +371,7 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (have_next) {
           mbar_wait(&bars->q_full[st ^ 1], ((it + 1) >> 1) & 1);
           tc_fence_after();
-          issue_S(st ^ 1);
+          issue_S(st ^ 1, it + 1);
           umma_commit(&bars->s_full);
         }
         mbar_wait(&bars->ds_ready, it & 1);
@@ -371,7 +461,7 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int q0 = (i_begin + it) * kTile;
       const int st = it & 1;
       const float* stat = sStat + st * 2 * kTile + hf * 64;
-      mbar_wait(&bars->stat_full[st], (it >> 1) & 1);
+      if constexpr (!kFold) mbar_wait(&bars->stat_full[st], (it >> 1) & 1);
       mbar_wait(&bars->s_full, it & 1);
       tc_fence_after();
       float pr[64];
@@ -384,13 +474,18 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // visible iff key <= q + off  <=>  q >= key - off ; whole block visible when q0 + off >= k0 + 127
       const bool need_mask = p.causal && (q0 + p.causal_off < k0 + kTile - 1);
       const int qmin = key - p.causal_off - q0 - hf * 64;  // first visible column index (local to this half)
+      if constexpr (kFold) {  // the tensor core already subtracted lse/scale per column
 #pragma unroll
-      for (int c4 = 0; c4 < 16; ++c4) {
-        const float4 l2 = *reinterpret_cast<const float4*>(stat + c4 * 4);
-        pr[c4 * 4 + 0] = ex2(fmaf(pr[c4 * 4 + 0], scale_log2, -l2.x));
-        pr[c4 * 4 + 1] = ex2(fmaf(pr[c4 * 4 + 1], scale_log2, -l2.y));
-        pr[c4 * 4 + 2] = ex2(fmaf(pr[c4 * 4 + 2], scale_log2, -l2.z));
-        pr[c4 * 4 + 3] = ex2(fmaf(pr[c4 * 4 + 3], scale_log2, -l2.w));
+        for (int c = 0; c < 64; ++c) pr[c] = ex2(pr[c] * scale_log2);
+      } else {
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) {
+          const float4 l2 = *reinterpret_cast<const float4*>(stat + c4 * 4);
+          pr[c4 * 4 + 0] = ex2(fmaf(pr[c4 * 4 + 0], scale_log2, -l2.x));
+          pr[c4 * 4 + 1] = ex2(fmaf(pr[c4 * 4 + 1], scale_log2, -l2.y));
+          pr[c4 * 4 + 2] = ex2(fmaf(pr[c4 * 4 + 2], scale_log2, -l2.z));
+          pr[c4 * 4 + 3] = ex2(fmaf(pr[c4 * 4 + 3], scale_log2, -l2.w));
+        }
       }
       if (!key_valid) {
 #pragma unroll
@@ -422,7 +517,8 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_wait_ld();
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 dl = *reinterpret_cast<const float4*>(stat + kTile + half * 32 + c4 * 4);
+          float4 dl = make_float4(0.f, 0.f, 0.f, 0.f);  // kFold: the tensor core already subtracted delta
+          if constexpr (!kFold) dl = *reinterpret_cast<const float4*>(stat + kTile + half * 32 + c4 * 4);
           const int c = half * 32 + c4 * 4;
           const float d0 = pr[c + 0] * (__uint_as_float(dp[c4 * 4 + 0]) - dl.x);
           const float d1 = pr[c + 1] * (__uint_as_float(dp[c4 * 4 + 1]) - dl.y);
@@ -484,10 +580,10 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 12) tmem_dealloc(tmem_base, 512);
 }
 
-template <bool kBF16>
+template <bool kBF16, bool kFold>
 static int launch_bwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                       const CUtensorMap& tmDO, const CUtensorMap& tmDQ, const BwdParams& p, cudaStream_t stream) {
-  auto kern = bwd_chunk_kernel<kBF16>;
+  auto kern = bwd_chunk_kernel<kBF16, kFold>;
   BA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes));
   dim3 grid((p.Sk + kTile - 1) / kTile, p.H, p.B);
   kern<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(tmQ, tmK, tmV, tmDO, tmDQ, p);
@@ -571,6 +667,7 @@ extern "C" int ba_bwd_chunk(ba_tensor4 d_o, ba_tensor4 q, ba_tensor4 k, ba_tenso
   p.B = B, p.Sq = Sq, p.Sk = Sk, p.H = H;
   p.scale = scale;
   p.scale_log2 = scale * kBwdLog2e;
+  p.inv_scale = 1.f / scale;
   p.causal = mask_mode == BA_MASK_CAUSAL;
   p.causal_off = causal_offset;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -585,6 +682,14 @@ extern "C" int ba_bwd_chunk(ba_tensor4 d_o, ba_tensor4 q, ba_tensor4 k, ba_tenso
       return BA_ERR_CUDA;
     }
   }
-  return dtype == BA_DTYPE_BF16 ? launch_bwd<true>(tmQ, tmK, tmV, tmDO, tmDQ, p, st)
-                                : launch_bwd<false>(tmQ, tmK, tmV, tmDO, tmDQ, p, st);
+  // BA_BWD_FOLD=0 (A/B knob, read once): row statistics through shared memory instead of the extra K steps
+  static const bool fold = [] {
+    const char* e = getenv("BA_BWD_FOLD");
+    return !e || atoi(e) != 0;
+  }();
+  if (fold)
+    return dtype == BA_DTYPE_BF16 ? launch_bwd<true, true>(tmQ, tmK, tmV, tmDO, tmDQ, p, st)
+                                  : launch_bwd<false, true>(tmQ, tmK, tmV, tmDO, tmDQ, p, st);
+  return dtype == BA_DTYPE_BF16 ? launch_bwd<true, false>(tmQ, tmK, tmV, tmDO, tmDQ, p, st)
+                                : launch_bwd<false, false>(tmQ, tmK, tmV, tmDO, tmDQ, p, st);
 }
