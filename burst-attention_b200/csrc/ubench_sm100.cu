@@ -64,14 +64,26 @@ __global__ void __launch_bounds__(kUbThreads, 1) ubench_kernel(int mode, int ite
     const uint64_t b0 = make_smem_desc(smem_u32(smem + kUbOffB), 16, 1024);
     const uint32_t box_b = N * 128;  // bytes of one 64-column SW128 box of B (N rows x 128 B)
     const int n = mode == 12 ? 1 : iters;
+    // lean issue path (descriptor halves as constants, 8 k-steps unrolled) so that the chain measures the tensor
+    // pipe and its operand fetch, not this warp's address arithmetic (the first version of this loop was
+    // issue-bound at ~109 clk per SS dispatch and ~80 per TS dispatch whatever N was)
+    const uint32_t a_lo0 = (smem_u32(smem + kUbOffA) >> 4) + desc_lo_lbo(16);
+    const uint32_t b_lo0 = (smem_u32(smem + kUbOffB) >> 4) + desc_lo_lbo(16);
+    constexpr uint32_t hi = desc_hi(1024);
     const long long t0 = clk();
-    for (int i = 0; i < n; ++i) {
-      const int kk = i & 7;
-      const uint32_t offa = (kk >> 2) * 16384 + (kk & 3) * 32, offb = (kk >> 2) * box_b + (kk & 3) * 32;
-      if (ts)
-        umma_ts(tb, tb + 256 + kk * 8, desc_advance(b0, offb), idesc, 1);
-      else
-        umma_ss(tb, desc_advance(a0, offa), desc_advance(b0, offb), idesc, 1);
+    if (n == 1) {
+      umma_ss_lh(tb, a_lo0, hi, b_lo0, hi, idesc, 1);
+    } else {
+      for (int i = 0; i < n; i += 8) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t offa = ((kk >> 2) * 16384 + (kk & 3) * 32) >> 4, offb = ((kk >> 2) * box_b + (kk & 3) * 32) >> 4;
+          if (ts)
+            umma_ts_lh(tb, tb + 256 + kk * 8, b_lo0 + offb, hi, idesc, 1);
+          else
+            umma_ss_lh(tb, a_lo0 + offa, hi, b_lo0 + offb, hi, idesc, 1);
+        }
+      }
     }
     umma_commit(&bars->mma_done);
     mbar_wait(&bars->mma_done, 0);

@@ -62,3 +62,37 @@ def test_causal_requires_cuda_flash_like_reference():
     q = torch.randn(1, 128, 1, 128, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(AssertionError):
         burst_attn_func(q, q, q, None, "triton", True)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_packed_qkv_wrappers_match_oracle(causal):
+    """flash_attn_func / _kvpacked_func / _qkvpacked_func (reference flash_triton.py:1013-1160): single-GPU entry
+    points over the same tile kernels, operands read through strided views of the packed tensors."""
+    from burst_attn.flash_triton import flash_attn_func, flash_attn_kvpacked_func, flash_attn_qkvpacked_func
+    torch.manual_seed(4)
+    dtype = torch.bfloat16
+    b, s, n, d = 2, 384, 3, 128
+    qkv = torch.randn(b, s, 3, n, d, device="cuda", dtype=dtype)
+    do = torch.randn(b, s, n, d, device="cuda", dtype=dtype)
+    q, k, v = (qkv[:, :, i].contiguous() for i in range(3))
+    o_ref, _, dq_ref, dk_ref, dv_ref = orc.dense_attention_bwd(q.cpu(), k.cpu(), v.cpu(), do.cpu(), None, causal)
+
+    p = qkv.clone().requires_grad_()
+    o = flash_attn_qkvpacked_func(p, None, causal)
+    (dqkv,) = torch.autograd.grad(o, (p,), do)
+    torch.testing.assert_close(o.double().cpu(), o_ref, **TOL[dtype])
+    for i, r in enumerate((dq_ref, dk_ref, dv_ref)):
+        torch.testing.assert_close(dqkv[:, :, i].double().cpu(), r, **TOL[dtype])
+
+    qq, kv = q.clone().requires_grad_(), qkv[:, :, 1:].clone().requires_grad_()
+    o = flash_attn_kvpacked_func(qq, kv, None, causal)
+    dq, dkv = torch.autograd.grad(o, (qq, kv), do)
+    torch.testing.assert_close(dq.double().cpu(), dq_ref, **TOL[dtype])
+    torch.testing.assert_close(dkv[:, :, 0].double().cpu(), dk_ref, **TOL[dtype])
+    torch.testing.assert_close(dkv[:, :, 1].double().cpu(), dv_ref, **TOL[dtype])
+
+    qq, kk, vv = (t.clone().requires_grad_() for t in (q, k, v))
+    o = flash_attn_func(qq, kk, vv, None, causal)
+    torch.testing.assert_close(o.double().cpu(), o_ref, **TOL[dtype])
+    with pytest.raises(NotImplementedError):
+        flash_attn_func(qq, kk, vv, torch.zeros(1, n, s, s, device="cuda"), causal)
