@@ -553,12 +553,16 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
     # ---- A/B: the same step with the ring replaced by a local buffer swap -> exposed ring-communication time
     ab = None
     if args.ab_comm and world > 1:
+        prev_tr = os.environ.get("BA_RING_TRANSPORT")
         os.environ["BA_RING_TRANSPORT"] = "local"
         try:
             step(q, k, v, do)
             ms_local = timed(lambda: step(q, k, v, do), K)
         finally:
-            os.environ.pop("BA_RING_TRANSPORT", None)
+            if prev_tr is None:
+                os.environ.pop("BA_RING_TRANSPORT", None)
+            else:
+                os.environ["BA_RING_TRANSPORT"] = prev_tr
         ab = {"ms_per_step_ring": ms_step, "ms_per_step_local_swap": ms_local,
               "exposed_comm_frac": max(0.0, (ms_step - ms_local) / ms_step),
               "how": "BA_RING_TRANSPORT=local: every hop is a device-local copy src->dst on the compute stream"}
@@ -577,7 +581,7 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"burst_attn_func fwd+bwd, bs={Bn} S={S} (S_local={S_loc}) H=32 d=128 bf16 "
                                    f"{'causal zigzag' if args.causal else 'non-causal contiguous'} shards, "
-                                   f"{'local kernel, no ring' if world == 1 else f'{world}-rank ring over NCCL'}"
+                                   f"{'local kernel, no ring' if world == 1 else f'{world}-rank ring over ' + ('copy engines + CUDA IPC' if os.environ.get('BA_RING_TRANSPORT') == 'ce' else 'NCCL')}"
                                    f"{f' (double ring, intra {args.double_ring})' if args.double_ring and world > 1 else ''}",
                        "global_batch": Bn, "seq_len": S, "parallelism": f"sp{world}",
                        "l2": "inputs (>= 256 MiB per tensor per rank) exceed the 126 MB L2; no flush needed"},

@@ -487,17 +487,18 @@ def _prepare(ctx, q, k, v, softmax_scale, flash, causal, optimize_bwd_comm, dete
 
 
 def _pad_head_dim(ops, tensors):
-    """The sm_100a tile kernels are built for head_dim 128 (``ops.tile_head_dim``).  A smaller head_dim
-    (the reference's CPU-runnable configuration C1 has 64) is run exactly by zero-padding the last axis
-    once per call: padded Q/K columns add 0 to every score, padded V columns produce output columns that
-    are exactly 0 and are sliced off, and the same holds for dO -> dQ/dK/dV.  Costs one copy per tensor
-    and runs the tile at D/128 of its efficiency; a native 64-wide tile is future work."""
-    tile = getattr(ops, "tile_head_dim", None)
+    """The sm_100a tile kernels exist for head_dim 64 and 128 (``ops.tile_head_dims``; the reference's
+    CPU-runnable configuration C1 has 64, its benchmarks 128).  Any other head_dim <= 128 is run exactly by
+    zero-padding the last axis once per call up to the next tile width: padded Q/K columns add 0 to every score,
+    padded V columns produce output columns that are exactly 0 and are sliced off, and the same holds for
+    dO -> dQ/dK/dV."""
+    tiles = getattr(ops, "tile_head_dims", None)
     D = tensors[0].shape[-1]
-    if tile is None or D == tile:
+    if tiles is None or D in tiles:
         return tensors, D
-    assert D < tile, f"head_dim {D} > {tile} is not supported"
-    return [torch.nn.functional.pad(t, (0, tile - D)) for t in tensors], D
+    bigger = [t for t in tiles if t > D]
+    assert bigger, f"head_dim {D} > {max(tiles)} is not supported"
+    return [torch.nn.functional.pad(t, (0, min(bigger) - D)) for t in tensors], D
 
 
 def _unpad(t, D):
@@ -506,14 +507,14 @@ def _unpad(t, D):
 
 def _op_forward(ctx, q, k, v, mode):
     ctx.host = False
-    if q.device.type == "cpu":
+    if q.device.type == "cpu" and getattr(get_ops(), "name", "") == "sm100":  # (tests inject CPU chunk operators)
         # host-resident operands (pinned CPU tensors, one rank): copies stream under the kernels (host_stream.py)
         from . import host_stream
         if not host_stream.is_host_call(q, k, v):
             raise TypeError("burst_attn_b200 needs CUDA tensors (or pinned CPU tensors on a CUDA machine); there is "
                             "no CPU implementation")
         assert ctx.topo.W == 1, "host-resident operands are supported on a single rank only (pass device tensors)"
-        assert q.shape[-1] == getattr(get_ops(), "tile_head_dim", q.shape[-1]), "host-resident operands need head_dim 128"
+        assert q.shape[-1] in getattr(get_ops(), "tile_head_dims", (q.shape[-1],)), "host-resident operands need head_dim 64 or 128"
         ctx.host, ctx.mode, ctx.head_dim = True, mode, q.shape[-1]
         o_host, saved = host_stream.forward(q, k, v, ctx.softmax_scale, ctx.seq_dim, mode != "none", _l2_block())
         ctx.save_for_backward(*saved)

@@ -24,7 +24,7 @@ def _dims(t: torch.Tensor, seq_dim: int):
 
 class NativeOps:
     name = "sm100"
-    tile_head_dim = 128  # the tile kernels' head_dim; the drivers zero-pad smaller ones (burst_attn_interface.py)
+    tile_head_dims = (64, 128)  # head dims the tile kernels are built for; the drivers zero-pad others up
 
     def __init__(self):
         self.lib = _n.lib()  # raises if the library is missing -- no fallback

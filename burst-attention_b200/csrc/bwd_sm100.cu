@@ -31,8 +31,8 @@ namespace ba {
 
 constexpr int kBwdThreads = 512;  // warps 0-7 compute, 8-11 dQ reduce, 12 MMA, 13 load, 14-15 idle (register donors)
 constexpr int kTile = 128;
-constexpr int kTileB = kTile * kTile * 2;  // 32 KiB 16-bit tile
-constexpr int kBoxB = kTileB / 2;          // 16 KiB: 128 rows x 64 cols SW128 box
+constexpr int kBoxB = kTile * 64 * 2;       // 16 KiB: 128 rows x 64 cols SW128 box
+constexpr int kDsTileB = kTile * kTile * 2;  // 32 KiB: the dS^T tile [128 keys][128 q], two boxes
 constexpr int kDqStageB = kTile * 32 * 4;  // 16 KiB: 128 rows x 32 fp32 cols SW128 box
 constexpr float kBwdLog2e = 1.4426950408889634f;
 
@@ -118,19 +118,26 @@ struct __align__(8) BwdBarriers {
 };
 
 // smem carve-up (bytes from the 1 KiB-aligned base)
-constexpr int kOffK = 0;
-constexpr int kOffV = kOffK + kTileB;
-constexpr int kOffQ = kOffV + kTileB;        // 2 stages
-constexpr int kOffDO = kOffQ + 2 * kTileB;   // 1 stage
-constexpr int kOffDS = kOffDO + kTileB;
-constexpr int kOffDQ = kOffDS + kTileB;      // 2 staging boxes
-constexpr int kOffStat = kOffDQ + 2 * kDqStageB;  // fold: [128 q rows][16 B] row-stat operand tile; else [2][lse2|delta] fp32
-constexpr int kOffFoldA = kOffStat + 2 * 2 * kTile * 4;  // fold: [ones(lse slots) 128 B][ones(delta slots) 128 B][zeros 128 B]
-constexpr int kOffBar = kOffFoldA + 512;
-constexpr int kBwdSmemBytes = kOffBar + 256;  // no align slack: the dynamic smem base is checked to be 1 KiB aligned
-static_assert(kBwdSmemBytes <= 232448, "backward kernel exceeds 227 KiB of shared memory");
+// head dim kD (64 or 128): an operand tile (K, V, Q, dO) is [128 rows][kD] = kD/64 boxes
+template <int kD>
+struct BwdLayout {
+  static_assert(kD == 64 || kD == 128, "head dim 64 or 128");
+  static constexpr int kTileB = kTile * kD * 2;
+  static constexpr int kBoxes = kD / 64;
+  static constexpr int kOffK = 0;
+  static constexpr int kOffV = kOffK + kTileB;
+  static constexpr int kOffQ = kOffV + kTileB;        // 2 stages
+  static constexpr int kOffDO = kOffQ + 2 * kTileB;   // 1 stage
+  static constexpr int kOffDS = kOffDO + kTileB;
+  static constexpr int kOffDQ = kOffDS + kDsTileB;    // 2 staging boxes
+  static constexpr int kOffStat = kOffDQ + 2 * kDqStageB;  // fold: [128 q rows][16 B] row-stat operand tile; else [2][lse2|delta] fp32
+  static constexpr int kOffFoldA = kOffStat + 2 * 2 * kTile * 4;  // fold: [ones(lse) 128 B][ones(delta) 128 B][zeros 128 B]
+  static constexpr int kOffBar = kOffFoldA + 512;
+  static constexpr int kSmemBytes = kOffBar + 256;  // no align slack: the dynamic smem base is checked to be 1 KiB aligned
+  static_assert(kSmemBytes <= 232448, "backward kernel exceeds 227 KiB of shared memory");
+};
 
-template <bool kBF16, bool kFold>
+template <bool kBF16, bool kFold, int kD>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -138,6 +145,10 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B atoms need a 1 KiB-aligned base
+  using L = BwdLayout<kD>;
+  constexpr int kTileB = L::kTileB, kBoxes = L::kBoxes, kKSteps = kD / 16, kChunks = kD / 32;
+  constexpr int kOffK = L::kOffK, kOffV = L::kOffV, kOffQ = L::kOffQ, kOffDO = L::kOffDO, kOffDS = L::kOffDS,
+                kOffDQ = L::kOffDQ, kOffStat = L::kOffStat, kOffFoldA = L::kOffFoldA, kOffBar = L::kOffBar;
   uint8_t* sK = smem + kOffK;
   uint8_t* sV = smem + kOffV;
   uint8_t* sQ = smem + kOffQ;
@@ -220,7 +231,7 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     reg_dec<64>();
     if (lane == 0) {
       mbar_arrive_expect_tx(&bars->kv_full, 2 * kTileB);
-      for (int half = 0; half < 2; ++half) {
+      for (int half = 0; half < kBoxes; ++half) {
         tma_load_4d(sK + half * kBoxB, &tmK, &bars->kv_full, half * 64, h, k0, b);
         tma_load_4d(sV + half * kBoxB, &tmV, &bars->kv_full, half * 64, h, k0, b);
       }
@@ -244,7 +255,7 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_wait(&bars->q_empty[st], ((it >> 1) & 1) ^ 1);  // also: the compute warps are done with stat stage st
       if (lane == 0) {
         mbar_arrive_expect_tx(&bars->q_full[st], kTileB);
-        for (int half = 0; half < 2; ++half)
+        for (int half = 0; half < kBoxes; ++half)
           tma_load_4d(sQ + st * kTileB + half * kBoxB, &tmQ, &bars->q_full[st], half * 64, h, q0, b);
       }
       if constexpr (kFold) {
@@ -281,7 +292,7 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (lane == 0) {
         mbar_wait(&bars->do_empty, (it & 1) ^ 1);
         mbar_arrive_expect_tx(&bars->do_full, kTileB);
-        for (int half = 0; half < 2; ++half)
+        for (int half = 0; half < kBoxes; ++half)
           tma_load_4d(sDO + half * kBoxB, &tmDO, &bars->do_full, half * 64, h, q0, b);
       }
       __syncwarp();
@@ -294,8 +305,8 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     reg_dec<64>();
     {
       constexpr uint32_t id_kk = make_idesc(kBF16, 128, 128, false, false);  // A K-major, B K-major
-      constexpr uint32_t id_kn = make_idesc(kBF16, 128, 128, false, true);   // A K-major/TMEM, B MN-major
-      constexpr uint32_t id_nn = make_idesc(kBF16, 128, 128, true, true);    // A MN-major, B MN-major
+      constexpr uint32_t id_kn = make_idesc(kBF16, 128, kD, false, true);    // A K-major/TMEM, B MN-major (N = d)
+      constexpr uint32_t id_nn = make_idesc(kBF16, 128, kD, true, true);     // A MN-major, B MN-major (N = d)
       const uint64_t dK_k = make_smem_desc(smem_u32(sK), 16, 1024);          // K tile as K-major A
       const uint64_t dV_k = make_smem_desc(smem_u32(sV), 16, 1024);
       const uint64_t dK_n = make_smem_desc(smem_u32(sK), kBoxB, 1024);       // K tile as MN-major B
@@ -316,7 +327,7 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       auto issue_S = [&](int st, int it_of_block) {  // S^T = K Q^T  (kFold: ... - lse/scale)
         const uint64_t dQ_k = make_smem_desc(smem_u32(sQ + st * kTileB), 16, 1024);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
+        for (int kk = 0; kk < kKSteps; ++kk)
           umma_ss(tS, desc_advance(dK_k, kstep_k(kk)), desc_advance(dQ_k, kstep_k(kk)), id_kk, kk > 0);
         if constexpr (kFold) {
           mbar_wait(&bars->stat_full[0], it_of_block & 1);
@@ -326,7 +337,7 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       };
       auto issue_dP = [&]() {  // dP^T = V dO^T  (kFold: ... - delta; same operand tile as the S^T just issued)
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
+        for (int kk = 0; kk < kKSteps; ++kk)
           umma_ss(tDP, desc_advance(dV_k, kstep_k(kk)), desc_advance(dDO_k, kstep_k(kk)), id_kk, kk > 0);
         if constexpr (kFold) umma_ss(tDP, dA_dl, dB_stat, id_kk, 1);
       };
@@ -404,9 +415,9 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_after();
       // whole dQ row -> registers, then hand the TMEM region straight back to the MMA warp
       // (the next dP^T is waiting for it); staging to smem / TMA happens from registers
-      uint32_t v[128];
+      uint32_t v[kD];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_x32(tDP + lane_base + c * 32, v + c * 32);
+      for (int c = 0; c < kChunks; ++c) tmem_ld_x32(tDP + lane_base + c * 32, v + c * 32);
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
@@ -419,7 +430,7 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         while (ld_acquire_gpu(turn) != kb) __nanosleep(64);
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < kChunks; ++c) {
         uint8_t* stage = sDQ + (c & 1) * kDqStageB;
         if (issuer) tma_store_wait_read<1>();  // the reduce that last read this staging box has finished
         named_bar_sync(1, 128);
@@ -553,11 +564,11 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int64_t sb = which == 0 ? p.dk_sb : p.dv_sb, ss = which == 0 ? p.dk_ss : p.dv_ss,
                     sh = which == 0 ? p.dk_sh : p.dv_sh;
       const float mul = which == 0 ? p.scale : 1.f;
-      float* dst = base + (int64_t)b * sb + (int64_t)key * ss + (int64_t)h * sh + hf * 64;
+      float* dst = base + (int64_t)b * sb + (int64_t)key * ss + (int64_t)h * sh + hf * (kD / 2);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < kD / 64; ++c) {
         uint32_t v[32];
-        tmem_ld_x32((which == 0 ? tDK : tDV) + lane_base + hf * 64 + c * 32, v);
+        tmem_ld_x32((which == 0 ? tDK : tDV) + lane_base + hf * (kD / 2) + c * 32, v);
         tmem_wait_ld();
         if (key_valid) {
 #pragma unroll
@@ -580,15 +591,23 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 12) tmem_dealloc(tmem_base, 512);
 }
 
-template <bool kBF16, bool kFold>
+template <bool kBF16, bool kFold, int kD>
 static int launch_bwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                       const CUtensorMap& tmDO, const CUtensorMap& tmDQ, const BwdParams& p, cudaStream_t stream) {
-  auto kern = bwd_chunk_kernel<kBF16, kFold>;
-  BA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes));
+  auto kern = bwd_chunk_kernel<kBF16, kFold, kD>;
+  constexpr int smem = BwdLayout<kD>::kSmemBytes;
+  BA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((p.Sk + kTile - 1) / kTile, p.H, p.B);
-  kern<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(tmQ, tmK, tmV, tmDO, tmDQ, p);
+  kern<<<grid, kBwdThreads, smem, stream>>>(tmQ, tmK, tmV, tmDO, tmDQ, p);
   BA_CHECK_CUDA(cudaGetLastError());
   return BA_OK;
+}
+
+template <bool kFold, int kD>
+static int launch_bwd_dt(int dtype, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                         const CUtensorMap& tmDO, const CUtensorMap& tmDQ, const BwdParams& p, cudaStream_t stream) {
+  return dtype == BA_DTYPE_BF16 ? launch_bwd<true, kFold, kD>(tmQ, tmK, tmV, tmDO, tmDQ, p, stream)
+                                : launch_bwd<false, kFold, kD>(tmQ, tmK, tmV, tmDO, tmDQ, p, stream);
 }
 
 // Deterministic-mode workspace (turn counters + tickets), one per (device, stream), grown on demand, zeroed on
@@ -637,7 +656,7 @@ extern "C" int ba_bwd_chunk(ba_tensor4 d_o, ba_tensor4 q, ba_tensor4 k, ba_tenso
                             int Sk, int H, int D, float scale, int mask_mode, int causal_offset, int flags, int dtype,
                             void* stream) {
   using namespace ba;
-  BA_REQUIRE(D == kTile, "ba_bwd_chunk: head dim %d unsupported (only 128)", D);
+  BA_REQUIRE(D == 128 || D == 64, "ba_bwd_chunk: head dim %d unsupported (64 or 128)", D);
   BA_REQUIRE(B > 0 && Sq > 0 && Sk > 0 && H > 0, "ba_bwd_chunk: empty problem B=%d Sq=%d Sk=%d H=%d", B, Sq, Sk, H);
   BA_REQUIRE(dtype == BA_DTYPE_FP16 || dtype == BA_DTYPE_BF16, "ba_bwd_chunk: bad dtype %d", dtype);
   BA_REQUIRE(mask_mode == BA_MASK_NONE || mask_mode == BA_MASK_CAUSAL, "ba_bwd_chunk: bad mask mode %d", mask_mode);
@@ -687,9 +706,9 @@ extern "C" int ba_bwd_chunk(ba_tensor4 d_o, ba_tensor4 q, ba_tensor4 k, ba_tenso
     const char* e = getenv("BA_BWD_FOLD");
     return !e || atoi(e) != 0;
   }();
-  if (fold)
-    return dtype == BA_DTYPE_BF16 ? launch_bwd<true, true>(tmQ, tmK, tmV, tmDO, tmDQ, p, st)
-                                  : launch_bwd<false, true>(tmQ, tmK, tmV, tmDO, tmDQ, p, st);
-  return dtype == BA_DTYPE_BF16 ? launch_bwd<true, false>(tmQ, tmK, tmV, tmDO, tmDQ, p, st)
-                                : launch_bwd<false, false>(tmQ, tmK, tmV, tmDO, tmDQ, p, st);
+  if (D == 64)
+    return fold ? launch_bwd_dt<true, 64>(dtype, tmQ, tmK, tmV, tmDO, tmDQ, p, st)
+                : launch_bwd_dt<false, 64>(dtype, tmQ, tmK, tmV, tmDO, tmDQ, p, st);
+  return fold ? launch_bwd_dt<true, 128>(dtype, tmQ, tmK, tmV, tmDO, tmDQ, p, st)
+              : launch_bwd_dt<false, 128>(dtype, tmQ, tmK, tmV, tmDO, tmDQ, p, st);
 }

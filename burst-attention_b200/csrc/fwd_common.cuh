@@ -8,11 +8,9 @@ namespace ba {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockN = 128;
-constexpr int kHeadDim = 128;
 constexpr int kKStages = 2;
 constexpr int kVStages = 2;
-constexpr int kTileBytes = kBlockN * kHeadDim * 2;  // 32 KiB: one 128x128 16-bit tile
-constexpr int kBoxBytes = kTileBytes / 2;           // 16 KiB: one 128 x 64 SW128 TMA box
+constexpr int kBoxBytes = 128 * 64 * 2;  // 16 KiB: one 128 x 64 SW128 TMA box (a [128][head_dim] tile is head_dim/64 boxes)
 constexpr int kFwdThreads = 320;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;

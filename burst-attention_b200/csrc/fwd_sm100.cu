@@ -41,21 +41,31 @@ struct __align__(8) FwdBarriers {
 
 constexpr int kSub = 64;  // keys per softmax sub-tile (S is double-buffered per Q tile in 64-column halves)
 static_assert(kKStages == 2 && kVStages == 2, "the unrolled MMA issue loop assumes 2-stage K/V rings");
-constexpr uint32_t kOffQ = 0;
-constexpr uint32_t kOffK = 2 * kTileBytes;
-constexpr uint32_t kOffV = kOffK + kKStages * kTileBytes;
-constexpr uint32_t kOffBars = kOffV + kVStages * kTileBytes;
-constexpr int kFwdSmemBytes = kOffBars + 256 /*barriers*/;
+// shared-memory carve-up for head dim kD (64 or 128): a tile is [128 rows][kD] 16-bit = kD/64 SW128 boxes of
+// [128 rows][64 cols] (16 KiB each)
+template <int kD>
+struct FwdLayout {
+  static_assert(kD == 64 || kD == 128, "head dim 64 or 128");
+  static constexpr uint32_t kTileB = 128 * kD * 2;
+  static constexpr int kBoxes = kD / 64;
+  static constexpr uint32_t kOffQ = 0;
+  static constexpr uint32_t kOffK = 2 * kTileB;
+  static constexpr uint32_t kOffV = kOffK + kKStages * kTileB;
+  static constexpr uint32_t kOffBars = kOffV + kVStages * kTileB;
+  static constexpr int kSmemBytes = kOffBars + 256 /*barriers*/;
+};
 
 // One step (sub-tile j, with U = j & 3 known at compile time so that every TMEM address, smem
 // descriptor and barrier address below is a constant): PV for both Q tiles on sub-tile j, then the
 // QK^T of sub-tile j+2 into the S buffers that PV just released.  sb16 = (smem base address) >> 4.
-template <bool kBF16, int U>
+template <bool kBF16, int kD, int U>
 __device__ __forceinline__ void fwd_mma_step(int j, uint32_t sb16, FwdBarriers* bars, int n_s0, int n_s1, int n_sub,
                                              bool load_state) {
+  using L = FwdLayout<kD>;
+  constexpr uint32_t kOffQ = L::kOffQ, kOffK = L::kOffK, kOffV = L::kOffV, kTileBytes = L::kTileB;
   constexpr int sub = U & 1, st = U >> 1, st_next = st ^ 1;
   constexpr uint32_t idesc_qk = make_idesc(kBF16, kBlockM, kSub, false, false);
-  constexpr uint32_t idesc_pv = make_idesc(kBF16, kBlockM, kHeadDim, false, true);
+  constexpr uint32_t idesc_pv = make_idesc(kBF16, kBlockM, kD, false, true);
   constexpr uint32_t hi = desc_hi(1024);
   const int tile = j >> 1;
   if (sub == 0) {
@@ -90,7 +100,7 @@ __device__ __forceinline__ void fwd_mma_step(int j, uint32_t sb16, FwdBarriers* 
         const uint32_t a_lo = sb16 + ((kOffQ + w * kTileBytes) >> 4) + desc_lo_lbo(16);
         const uint32_t k_lo = sb16 + ((kOffK + st_next * kTileBytes + sub * kSub * 128) >> 4) + desc_lo_lbo(16);
 #pragma unroll
-        for (int kk = 0; kk < kHeadDim / 16; ++kk) {
+        for (int kk = 0; kk < kD / 16; ++kk) {
           const uint32_t off = ((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4;
           umma_ss_lh(tS, a_lo + off, hi, k_lo + off, hi, idesc_qk, kk > 0 ? 1u : 0u);
         }
@@ -109,19 +119,20 @@ __device__ __forceinline__ int fwd_trip_count(int r0, const FwdParams& p) {
   return max_limit < 0 ? 0 : max_limit / kSub + 1;
 }
 
-// kPoly: every kPoly-th exponential of a row is evaluated with ex2_poly on the FMA pipe instead of
-// MUFU.EX2 (0 = all on MUFU); MUFU (16/clk/SM) is co-critical with the tensor pipe in this kernel.
-template <bool kBF16, int kPoly>
+template <bool kBF16, int kD>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();      // SWIZZLE_128B atoms need a 1 KiB-aligned base
-  uint8_t* sQ = smem + kOffQ;                       // [2][32 KiB]
-  uint8_t* sK = smem + kOffK;                       // [kKStages][32 KiB]
-  uint8_t* sV = smem + kOffV;                       // [kVStages][32 KiB]
-  FwdBarriers* bars = reinterpret_cast<FwdBarriers*>(smem + kOffBars);
+  using L = FwdLayout<kD>;
+  constexpr uint32_t kOffQ = L::kOffQ, kOffK = L::kOffK, kOffV = L::kOffV, kTileBytes = L::kTileB;
+  constexpr int kBoxes = L::kBoxes, kChunks = kD / 32;  // 32-column fp32 chunks of an O row
+  uint8_t* sQ = smem + kOffQ;                       // [2][tile]
+  uint8_t* sK = smem + kOffK;                       // [kKStages][tile]
+  uint8_t* sV = smem + kOffV;                       // [kVStages][tile]
+  FwdBarriers* bars = reinterpret_cast<FwdBarriers*>(smem + L::kOffBars);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -177,20 +188,20 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (lane == 0) {
       mbar_arrive_expect_tx(&bars->q_full, 2 * kTileBytes);
       for (int w = 0; w < 2; ++w)
-        for (int half = 0; half < 2; ++half)
+        for (int half = 0; half < kBoxes; ++half)
           tma_load_4d(sQ + w * kTileBytes + half * kBoxBytes, &tmQ, &bars->q_full, half * 64, h,
                       row0 + w * kBlockM, b);
       for (int i = 0; i < n_tiles; ++i) {
         const int ks = i % kKStages, kph = (i / kKStages) & 1;
         mbar_wait(&bars->k_empty[ks], kph ^ 1);
         mbar_arrive_expect_tx(&bars->k_full[ks], kTileBytes);
-        for (int half = 0; half < 2; ++half)
+        for (int half = 0; half < kBoxes; ++half)
           tma_load_4d(sK + ks * kTileBytes + half * kBoxBytes, &tmK, &bars->k_full[ks], half * 64, h,
                       i * kBlockN, b);
         const int vs = i % kVStages, vph = (i / kVStages) & 1;
         mbar_wait(&bars->v_empty[vs], vph ^ 1);
         mbar_arrive_expect_tx(&bars->v_full[vs], kTileBytes);
-        for (int half = 0; half < 2; ++half)
+        for (int half = 0; half < kBoxes; ++half)
           tma_load_4d(sV + vs * kTileBytes + half * kBoxBytes, &tmV, &bars->v_full[vs], half * 64, h,
                       i * kBlockN, b);
       }
@@ -212,7 +223,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const uint32_t a_lo = sb16 + ((kOffQ + w * kTileBytes) >> 4) + desc_lo_lbo(16);
             const uint32_t k_lo = sb16 + ((kOffK + j * kSub * 128) >> 4) + desc_lo_lbo(16);
 #pragma unroll
-            for (int kk = 0; kk < kHeadDim / 16; ++kk) {
+            for (int kk = 0; kk < kD / 16; ++kk) {
               const uint32_t off = ((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4;
               umma_ss_lh(w * 128 + j * kSub, a_lo + off, hi, k_lo + off, hi, idesc_qk, kk > 0 ? 1u : 0u);
             }
@@ -224,10 +235,10 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     const bool ls = p.load_state != 0;
     for (int j0 = 0; j0 < n_sub; j0 += 4) {
-      fwd_mma_step<kBF16, 0>(j0, sb16, bars, n_s0, n_s1, n_sub, ls);
-      if (j0 + 1 < n_sub) fwd_mma_step<kBF16, 1>(j0 + 1, sb16, bars, n_s0, n_s1, n_sub, ls);
-      if (j0 + 2 < n_sub) fwd_mma_step<kBF16, 2>(j0 + 2, sb16, bars, n_s0, n_s1, n_sub, ls);
-      if (j0 + 3 < n_sub) fwd_mma_step<kBF16, 3>(j0 + 3, sb16, bars, n_s0, n_s1, n_sub, ls);
+      fwd_mma_step<kBF16, kD, 0>(j0, sb16, bars, n_s0, n_s1, n_sub, ls);
+      if (j0 + 1 < n_sub) fwd_mma_step<kBF16, kD, 1>(j0 + 1, sb16, bars, n_s0, n_s1, n_sub, ls);
+      if (j0 + 2 < n_sub) fwd_mma_step<kBF16, kD, 2>(j0 + 2, sb16, bars, n_s0, n_s1, n_sub, ls);
+      if (j0 + 3 < n_sub) fwd_mma_step<kBF16, kD, 3>(j0 + 3, sb16, bars, n_s0, n_s1, n_sub, ls);
     }
   } else {
     // ============================================================ softmax warps
@@ -255,7 +266,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         const float* src = p.o_acc + (int64_t)b * p.oacc_sb + (int64_t)row * p.oacc_ss + (int64_t)h * p.oacc_sh;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < kChunks; ++c) {
           uint32_t v[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -307,7 +318,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
             const float f = (m == -INFINITY) ? 0.f : ex2(m - m_new);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < kChunks; ++c) {
               uint32_t v[32];
               tmem_ld_x32(tO + c * 32, v);
               tmem_wait_ld();
@@ -328,7 +339,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const float p1 = ex2(fmaf(s[c + 1], scale_log2, neg_m));
           const float p2 = ex2(fmaf(s[c + 2], scale_log2, neg_m));
           const float x3 = fmaf(s[c + 3], scale_log2, neg_m);
-          const float p3 = (kPoly > 0 && ((c / 4) % (kPoly / 4 > 0 ? kPoly / 4 : 1)) == 0) ? ex2_poly(x3) : ex2(x3);
+          const float p3 = ex2(x3);
           sum0 += p0;
           sum1 += p1;
           sum2 += p2;
@@ -356,7 +367,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const float lse_out = l > 0.f ? (m + lg2(l)) * kLn2 : -INFINITY;
       if (valid_row) p.lse[(int64_t)b * p.lse_sb + (int64_t)h * p.lse_sh + row] = lse_out;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < kChunks; ++c) {
         uint32_t v[32];
         if (o_live) {
           tmem_ld_x32(tO + c * 32, v);
@@ -403,13 +414,14 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 
-template <bool kBF16, int kPoly>
+template <bool kBF16, int kD>
 static int launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const FwdParams& p,
                       cudaStream_t stream) {
-  auto kern = fwd_chunk_kernel<kBF16, kPoly>;
-  BA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+  auto kern = fwd_chunk_kernel<kBF16, kD>;
+  constexpr int smem = FwdLayout<kD>::kSmemBytes;
+  BA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((p.Sq + 2 * kBlockM - 1) / (2 * kBlockM), p.H, p.B);
-  kern<<<grid, kFwdThreads, kFwdSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+  kern<<<grid, kFwdThreads, smem, stream>>>(tmQ, tmK, tmV, p);
   BA_CHECK_CUDA(cudaGetLastError());
   return BA_OK;
 }
@@ -420,7 +432,7 @@ extern "C" int ba_fwd_chunk(ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_tensor4
                             ba_tensor4 o_out, int B, int Sq, int Sk, int H, int D, float scale, int mask_mode,
                             int causal_offset, int flags, int dtype, void* stream) {
   using namespace ba;
-  BA_REQUIRE(D == kHeadDim, "ba_fwd_chunk: head dim %d unsupported (only 128)", D);
+  BA_REQUIRE(D == 128 || D == 64, "ba_fwd_chunk: head dim %d unsupported (64 or 128)", D);
   BA_REQUIRE(B > 0 && Sq > 0 && Sk > 0 && H > 0, "ba_fwd_chunk: empty problem B=%d Sq=%d Sk=%d H=%d", B, Sq, Sk, H);
   BA_REQUIRE(dtype == BA_DTYPE_FP16 || dtype == BA_DTYPE_BF16, "ba_fwd_chunk: bad dtype %d", dtype);
   BA_REQUIRE(mask_mode == BA_MASK_NONE || mask_mode == BA_MASK_CAUSAL, "ba_fwd_chunk: bad mask mode %d", mask_mode);
@@ -460,17 +472,7 @@ extern "C" int ba_fwd_chunk(ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_tensor4
   p.load_state = first ? 0 : 1;
   p.store_lowp = last ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // BA_FWD_POLY (tuning knob, read once): 0 = all exponentials on MUFU, 4 = every 4th, 8 = every 8th on FMA
-  static const int poly = [] {
-    const char* e = getenv("BA_FWD_POLY");
-    return e ? atoi(e) : 0;
-  }();
-  if (dtype == BA_DTYPE_BF16) {
-    if (poly == 4) return launch_fwd<true, 4>(tmQ, tmK, tmV, p, st);
-    if (poly == 8) return launch_fwd<true, 8>(tmQ, tmK, tmV, p, st);
-    return launch_fwd<true, 0>(tmQ, tmK, tmV, p, st);
-  }
-  if (poly == 4) return launch_fwd<false, 4>(tmQ, tmK, tmV, p, st);
-  if (poly == 8) return launch_fwd<false, 8>(tmQ, tmK, tmV, p, st);
-  return launch_fwd<false, 0>(tmQ, tmK, tmV, p, st);
+  if (D == 64)
+    return dtype == BA_DTYPE_BF16 ? launch_fwd<true, 64>(tmQ, tmK, tmV, p, st) : launch_fwd<false, 64>(tmQ, tmK, tmV, p, st);
+  return dtype == BA_DTYPE_BF16 ? launch_fwd<true, 128>(tmQ, tmK, tmV, p, st) : launch_fwd<false, 128>(tmQ, tmK, tmV, p, st);
 }

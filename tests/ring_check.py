@@ -39,23 +39,19 @@ def _double_group(world, intra):
 def run_cases(rank, world, dev):
     n_heads = int(os.environ.get("RING_CHECK_HEADS", "8"))
     fails = 0
-    # RING_CHECK_DOUBLE=<intra size>: run every case over the hierarchical (double) ring as well.  Opt-in:
-    # that schedule is covered by the gloo tests (tests/test_ring_gloo.py); its NCCL transport has not yet
-    # had a multi-GPU session.
-    intra = int(os.environ.get("RING_CHECK_DOUBLE", "0"))
-    double_group = _double_group(world, intra) if intra and world % intra == 0 and 1 < intra < world else None
-    if double_group is not None:
-        os.environ["BA_DOUBLE_RING"] = "1"
-    for dg in ([None, None], double_group):
-        if dg is None:
-            continue
-        fails += _run_cases(rank, world, dev, n_heads, dg)
+    # RING_CHECK_DOUBLE=<intra sizes, comma list>: run every case over the hierarchical (double) ring as well
+    # (intra-node rings of L consecutive ranks, reference test/test_burst.py:120-156).
+    fails += _run_cases(rank, world, dev, n_heads, [None, None])
+    for tok in os.environ.get("RING_CHECK_DOUBLE", "").split(","):
+        intra = int(tok) if tok.strip() else 0
+        if intra and world % intra == 0 and 1 < intra < world:
+            os.environ["BA_DOUBLE_RING"] = "1"
+            fails += _run_cases(rank, world, dev, n_heads, _double_group(world, intra), f"double L={intra}")
     return fails
 
 
-def _run_cases(rank, world, dev, n_heads, double_group):
+def _run_cases(rank, world, dev, n_heads, double_group, tag="flat"):
     fails = 0
-    tag = "double" if double_group[0] is not None else "flat"
     for dtype, tol in ((torch.float16, dict(rtol=1e-3, atol=1e-2)), (torch.bfloat16, dict(rtol=1.6e-2, atol=2e-2))):
         for name, func, causal, layout in (("none", burst_attn_func, False, "contiguous"),
                                            ("zigzag", burst_attn_func, True, "zigzag"),
@@ -84,7 +80,7 @@ def _run_cases(rank, world, dev, n_heads, double_group):
             flag = torch.tensor([0 if ok else 1], device=dev)
             dist.all_reduce(flag)
             if rank == 0:
-                print(f"ring_check W={world} {tag:6s} {name:8s} {str(dtype):15s} {'PASS' if flag.item() == 0 else 'FAIL'}", flush=True)
+                print(f"ring_check W={world} {tag:10s} {os.environ.get('BA_RING_TRANSPORT', 'nccl'):4s} {name:8s} {str(dtype):15s} {'PASS' if flag.item() == 0 else 'FAIL'}", flush=True)
             fails += int(flag.item())
     return fails
 

@@ -1,6 +1,7 @@
 """BASELINE.json configs[0] (C1: the reference's own CPU-runnable case, B=1, S=4096, H=8, D=64) through the
-public API on one GPU.  head_dim 64 runs on the 128-wide tile by zero padding (burst_attn_interface.py
-``_pad_head_dim``); results must match dense attention on the unpadded tensors."""
+public API on one GPU.  head_dim 64 has its own tile (kernels templated on the head dim: one SW128 box per operand
+tile, 4 k-steps for QK^T / S^T / dP^T, N = 64 for PV / dV / dK / dQ); other head dims <= 128 are zero-padded up to
+the next tile width (burst_attn_interface.py ``_pad_head_dim``).  Results must match dense attention."""
 import pytest
 import torch
 
@@ -48,3 +49,51 @@ def test_normal_layout_head_dim_64_and_striped_32():
     torch.testing.assert_close(o.double().cpu(), o_ref, **TOL[torch.float16])
     for g, r in ((dv, dv_ref), (dk, dk_ref), (dq, dq_ref)):
         torch.testing.assert_close(g.double().cpu(), r, rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("D", [64, 128])
+def test_native_tile_is_used_for_64_and_128(D):
+    """No padding copy for the two native tile widths: the kernels see the user's tensors (same data_ptr)."""
+    from burst_attn import chunk_ops
+    from burst_attn.burst_attn_interface import _pad_head_dim
+    q = torch.randn(1, 256, 2, D, device="cuda", dtype=torch.bfloat16)
+    (qp,), d = _pad_head_dim(chunk_ops.get_ops(), [q])
+    assert qp.data_ptr() == q.data_ptr() and d == D
+    (q96,), d = _pad_head_dim(chunk_ops.get_ops(), [q[..., :40].contiguous()])
+    assert q96.shape[-1] == 64 and d == 40
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_head_dim_64_kernels_directly_with_carried_state_and_offsets(causal):
+    """ba_fwd_chunk / ba_bwd_chunk at D = 64: chained K/V chunks (carried state), ragged sizes, a causal offset."""
+    from burst_attn.chunk_ops import NativeOps
+    dtype = torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(3)
+    mk = lambda S: torch.randn(2, S, 3, 64, device="cuda", generator=g).to(dtype)  # noqa: E731
+    Sq, Sc = 300, 200
+    q, do = mk(Sq), mk(Sq)
+    ks, vs = [mk(Sc), mk(Sc)], [mk(Sc), mk(Sc)]
+    scale = 64 ** -0.5
+    ops = NativeOps()
+    out = torch.empty_like(q)
+    lse = torch.empty(2, 3, Sq, device="cuda", dtype=torch.float32)
+    o_acc = torch.empty(q.shape, device="cuda", dtype=torch.float32)
+    offs = [100, -100] if causal else [0, 0]
+    o_ref = l_ref = None
+    for c in range(2):
+        ops.fwd_chunk(q, ks[c], vs[c], o_acc, lse, out, scale, causal, offs[c], c == 0, c == 1, 1)
+        o_ref, l_ref = orc.chunk_forward(q.cpu(), ks[c].cpu(), vs[c].cpu(), o_ref, l_ref, scale,
+                                         ("causal_offset", offs[c]) if causal else "none")
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out.double().cpu(), o_ref, **TOL[dtype])
+    torch.testing.assert_close(lse.double().cpu(), l_ref, rtol=1e-3, atol=2e-3)
+    delta = torch.empty_like(lse)
+    ops.delta(out, do, delta, 1)
+    for c in range(2):
+        acc = [torch.zeros(t.shape, device="cuda", dtype=torch.float32) for t in (q, ks[c], vs[c])]
+        ops.bwd_chunk(do, q, ks[c], vs[c], delta, lse, acc[0], acc[1], acc[2], scale, causal, offs[c], 1)
+        torch.cuda.synchronize()
+        ref = orc.chunk_backward(do.cpu(), q.cpu(), ks[c].cpu(), vs[c].cpu(), orc.compute_delta(out.cpu(), do.cpu()),
+                                 l_ref, scale, ("causal_offset", offs[c]) if causal else "none")
+        for a, r in zip(acc, ref):
+            torch.testing.assert_close(a.double().cpu(), r, **TOL[dtype])

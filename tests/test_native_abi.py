@@ -52,7 +52,7 @@ def test_bad_arguments_return_error_string(nat):
     L = nat.lib()
     z4 = nat.ba_tensor4(None, 0, 0, 0)
     zr = nat.ba_rowstat(None, 0, 0)
-    rc = L.ba_fwd_chunk(z4, z4, z4, z4, zr, z4, 1, 128, 128, 1, 64, 1.0, 0, 0, 3, 1, None)
+    rc = L.ba_fwd_chunk(z4, z4, z4, z4, zr, z4, 1, 128, 128, 1, 96, 1.0, 0, 0, 3, 1, None)
     assert rc != 0 and b"head dim" in L.ba_last_error()
     rc = L.ba_fwd_chunk(z4, z4, z4, z4, zr, z4, 1, 128, 128, 1, 128, 1.0, 0, 0, 3, 1, None)
     assert rc != 0 and b"null" in L.ba_last_error()

@@ -249,14 +249,14 @@ def test_single_process_world1_cpu():
 
 
 def test_head_dim_padding_world1_cpu():
-    """head_dim below the tile's (128 on the GPU; 32 faked here) is zero-padded once per call by the
-    driver and sliced off again -- exact for O, dQ, dK, dV, both layouts."""
+    """A head_dim the tile kernels are not built for (64 and 128 on the GPU; (8, 32) faked here) is zero-padded
+    once per call by the driver up to the next tile width and sliced off again -- exact for O, dQ, dK, dV."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from burst_attn import burst_attn_func, burst_attn_func_striped, chunk_ops
     from oracle import attention_oracle as orc
     from oracle_ops import OracleOps
     ops = OracleOps()
-    ops.tile_head_dim = 32
+    ops.tile_head_dims = (8, 32)
     chunk_ops._set_ops_for_testing(ops)
     try:
         torch.manual_seed(5)
