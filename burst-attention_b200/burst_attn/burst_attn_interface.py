@@ -120,20 +120,29 @@ def _l2_block() -> int:
     return int(os.environ.get("BA_L2_BLOCK", "32768"))
 
 
-def _fwd_round(ops, q, k, v, o_acc, lse, out, scale, causal, off, first, last, seq_dim):
+def _bias_kw(bias, c0=None, n=None):
+    """Keyword for the chunk operators: the key-bias view of keys [c0, c0+n) (nothing when there is no bias, so
+    test operators without a bias parameter keep working)."""
+    if bias is None:
+        return {}
+    return {"bias": bias if c0 is None else bias.narrow(2, c0, n)}
+
+
+def _fwd_round(ops, q, k, v, o_acc, lse, out, scale, causal, off, first, last, seq_dim, bias=None):
     """One forward ring round, split over K/V blocks that fit L2 (each block is one kernel launch with
     the carried state; the state pass costs 2 x 512 B per row and head, the block > 8 MB of math)."""
     blk = _l2_block()
     Sq, Sk = q.shape[seq_dim], k.shape[seq_dim]
     if Sk <= blk + blk // 2:
-        ops.fwd_chunk(q, k, v, o_acc, lse, out, scale, causal, off, first, last, seq_dim)
+        ops.fwd_chunk(q, k, v, o_acc, lse, out, scale, causal, off, first, last, seq_dim, **_bias_kw(bias))
         return
     n = (Sk + blk - 1) // blk
     for c in range(n):
         c0 = c * blk
         kc, vc = k.narrow(seq_dim, c0, min(blk, Sk - c0)), v.narrow(seq_dim, c0, min(blk, Sk - c0))
         if not causal:
-            ops.fwd_chunk(q, kc, vc, o_acc, lse, out, scale, False, 0, first and c == 0, last and c == n - 1, seq_dim)
+            ops.fwd_chunk(q, kc, vc, o_acc, lse, out, scale, False, 0, first and c == 0, last and c == n - 1, seq_dim,
+                          **_bias_kw(bias, c0, min(blk, Sk - c0)))
             continue
         # causal: rows before r_start see none of this block's keys (key c0+b visible to row a iff
         # c0 + b <= a + off); keep r_start on a tile-pair boundary
@@ -142,7 +151,8 @@ def _fwd_round(ops, q, k, v, o_acc, lse, out, scale, causal, off, first, last, s
             break
         ops.fwd_chunk(q.narrow(seq_dim, r_start, Sq - r_start), kc, vc,
                       o_acc.narrow(seq_dim, r_start, Sq - r_start), lse.narrow(2, r_start, Sq - r_start), None,
-                      scale, True, r_start + off - c0, first and c == 0, False, seq_dim)
+                      scale, True, r_start + off - c0, first and c == 0, False, seq_dim,
+                      **_bias_kw(bias, c0, min(blk, Sk - c0)))
     if causal and last:
         ops.cast(o_acc, out, seq_dim)
 
@@ -152,26 +162,28 @@ def _fwd_round_needs_state(k, seq_dim) -> bool:
     return k.shape[seq_dim] > blk + blk // 2
 
 
-def _bwd_round(ops, g, q, k, v, delta, lse, dq_part, dk_acc, dv_acc, scale, causal, off, seq_dim, deterministic):
+def _bwd_round(ops, g, q, k, v, delta, lse, dq_part, dk_acc, dv_acc, scale, causal, off, seq_dim, deterministic,
+               bias=None):
     """One backward ring round, split over blocks of Q-bundle rows that fit L2."""
     blk = _l2_block()
     Sq, Sk = q.shape[seq_dim], k.shape[seq_dim]
     if Sq <= blk + blk // 2:
-        ops.bwd_chunk(g, q, k, v, delta, lse, dq_part, dk_acc, dv_acc, scale, causal, off, seq_dim, deterministic)
+        ops.bwd_chunk(g, q, k, v, delta, lse, dq_part, dk_acc, dv_acc, scale, causal, off, seq_dim, deterministic,
+                      **_bias_kw(bias))
         return
     for r0 in range(0, Sq, blk):
         n = min(blk, Sq - r0)
-        kk, vv, dk, dv, o2 = k, v, dk_acc, dv_acc, off
+        kk, vv, dk, dv, o2, bkw = k, v, dk_acc, dv_acc, off, _bias_kw(bias)
         if causal:
             kmax = min(Sk, r0 + n + off)  # keys visible to the last row of this block
             if kmax <= 0:
                 continue
-            kk, vv = k.narrow(seq_dim, 0, kmax), v.narrow(seq_dim, 0, kmax)
+            kk, vv, bkw = k.narrow(seq_dim, 0, kmax), v.narrow(seq_dim, 0, kmax), _bias_kw(bias, 0, kmax)
             dk, dv = dk_acc.narrow(seq_dim, 0, kmax), dv_acc.narrow(seq_dim, 0, kmax)
             o2 = off + r0
         ops.bwd_chunk(g.narrow(seq_dim, r0, n), q.narrow(seq_dim, r0, n), kk, vv, delta.narrow(2, r0, n),
                       lse.narrow(2, r0, n), dq_part.narrow(seq_dim, r0, n), dk, dv, scale, causal, o2, seq_dim,
-                      deterministic)
+                      deterministic, **bkw)
 
 
 def _check_inputs(q, k, v, seq_dim):

@@ -39,7 +39,8 @@ class ba_rowstat(ctypes.Structure):
 _lib = None
 
 _EXPORTS = (
-    "ba_last_error", "ba_device_check", "ba_version", "ba_fwd_chunk", "ba_bwd_delta", "ba_bwd_chunk",
+    "ba_last_error", "ba_device_check", "ba_version", "ba_fwd_chunk", "ba_fwd_chunk_bias", "ba_bwd_delta", "ba_bwd_chunk",
+    "ba_bwd_chunk_bias",
     "ba_cast_from_f32", "ba_accumulate_f32", "ba_ring_unique_id", "ba_ring_create", "ba_ring_post",
     "ba_ring_wait", "ba_ring_rank", "ba_ring_world", "ba_ring_destroy", "ba_ring_arena_create",
     "ba_ring_arena_connect",
@@ -70,6 +71,12 @@ def lib() -> ctypes.CDLL:
     L.ba_fwd_chunk.restype = i
     L.ba_fwd_chunk.argtypes = [ba_tensor4, ba_tensor4, ba_tensor4, ba_tensor4, ba_rowstat, ba_tensor4,
                                i, i, i, i, i, f, i, i, i, i, vp]
+    L.ba_fwd_chunk_bias.restype = i
+    L.ba_fwd_chunk_bias.argtypes = [ba_tensor4, ba_tensor4, ba_tensor4, ba_rowstat, ba_tensor4, ba_rowstat, ba_tensor4,
+                                    i, i, i, i, i, f, i, i, i, i, vp]
+    L.ba_bwd_chunk_bias.restype = i
+    L.ba_bwd_chunk_bias.argtypes = [ba_tensor4, ba_tensor4, ba_tensor4, ba_tensor4, ba_rowstat, ba_rowstat, ba_rowstat,
+                                    ba_tensor4, ba_tensor4, ba_tensor4, i, i, i, i, i, f, i, i, i, i, vp]
     L.ba_bwd_delta.restype = i
     L.ba_bwd_delta.argtypes = [ba_tensor4, ba_tensor4, ba_rowstat, i, i, i, i, i, vp]
     L.ba_bwd_chunk.restype = i
@@ -150,8 +157,10 @@ def t4(t: Optional[torch.Tensor], seq_dim: int) -> ba_tensor4:
     return ba_tensor4(t.data_ptr(), t.stride(0), t.stride(seq_dim), t.stride(3 - seq_dim))
 
 
-def rs(t: torch.Tensor) -> ba_rowstat:
-    """[B,H,S] fp32 row statistic (lse / delta); S contiguous."""
+def rs(t: Optional[torch.Tensor]) -> ba_rowstat:
+    """[B,H,S] fp32 row statistic (lse / delta / key bias); S contiguous.  None -> null view."""
+    if t is None:
+        return ba_rowstat(None, 0, 0)
     assert t.dim() == 3 and t.stride(2) == 1 and t.dtype == torch.float32
     return ba_rowstat(t.data_ptr(), t.stride(0), t.stride(1))
 

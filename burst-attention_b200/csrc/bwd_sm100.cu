@@ -56,33 +56,7 @@ __device__ __forceinline__ void reg_dec() {
 //     its second K chunk (k = 8..15) re-reads the first (LBO = 0): harmless, A is zero there;
 //   A (constant): ONE 128-byte core matrix of identical rows [1 1 1 0 0 0 0 0] (lse) or [0 0 0 1 1 1 0 0]
 //     (delta) shared by all 16 row groups (SBO = 0), second K chunk = a zero core matrix.
-BA_DEVICE uint64_t make_smem_desc_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell); swizzle field = 0: none
-  return d;
-}
-template <bool kBF16>
-BA_DEVICE uint32_t to16(float x) {
-  if constexpr (kBF16) return __bfloat16_as_ushort(__float2bfloat16_rn(x));
-  else return __half_as_ushort(__float2half_rn(x));
-}
-template <bool kBF16>
-BA_DEVICE float from16(uint32_t h) {
-  if constexpr (kBF16) return __bfloat162float(__ushort_as_bfloat16(static_cast<unsigned short>(h)));
-  else return __half2float(__ushort_as_half(static_cast<unsigned short>(h)));
-}
-template <bool kBF16>
-BA_DEVICE void split3(float x, uint32_t& h0, uint32_t& h1, uint32_t& h2) {
-  h0 = to16<kBF16>(x);
-  float r = x - from16<kBF16>(h0);
-  h1 = to16<kBF16>(r);
-  r -= from16<kBF16>(h1);
-  h2 = to16<kBF16>(r);
-}
-
+// (make_smem_desc_noswz / split3: sm100_ptx.cuh)
 struct BwdParams {
   const float* lse;
   int64_t lse_sb, lse_sh;
@@ -95,6 +69,8 @@ struct BwdParams {
   int B, Sq, Sk, H;
   float scale, scale_log2, inv_scale;
   int causal, causal_off;
+  const float* bias;  // optional additive bias per key [B|1, H, Sk] (fp32), or null
+  int64_t bias_sb, bias_sh;
   int* sem;     // deterministic mode: [B][H][nQ] turn counters ordering the dQ reductions by key block; else null
   int* ticket;  // deterministic mode: [B][H] key-block tickets (a CTA's key block = the order in which it STARTED)
 };
@@ -467,6 +443,11 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int key = k0 + r;
     const bool key_valid = key < p.Sk;
     const float scale_log2 = p.scale_log2;
+    // additive bias of this thread's key, in log2 units (scores = q k^T scale + bias[key]; reference lao.py:155-173,
+    // "vector" bias): a per-thread scalar in this key-row layout, folded into the exponent's FMA
+    const float bias2 = (p.bias && key_valid)
+                            ? __ldg(p.bias + (int64_t)b * p.bias_sb + (int64_t)h * p.bias_sh + key) * kBwdLog2e
+                            : 0.f;
     uint8_t* ds_row = sDS + hf * kBoxB + r * 128;
     for (int it = 0; it < n_it; ++it) {
       const int q0 = (i_begin + it) * kTile;
@@ -487,15 +468,15 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int qmin = key - p.causal_off - q0 - hf * 64;  // first visible column index (local to this half)
       if constexpr (kFold) {  // the tensor core already subtracted lse/scale per column
 #pragma unroll
-        for (int c = 0; c < 64; ++c) pr[c] = ex2(pr[c] * scale_log2);
+        for (int c = 0; c < 64; ++c) pr[c] = ex2(fmaf(pr[c], scale_log2, bias2));
       } else {
 #pragma unroll
         for (int c4 = 0; c4 < 16; ++c4) {
           const float4 l2 = *reinterpret_cast<const float4*>(stat + c4 * 4);
-          pr[c4 * 4 + 0] = ex2(fmaf(pr[c4 * 4 + 0], scale_log2, -l2.x));
-          pr[c4 * 4 + 1] = ex2(fmaf(pr[c4 * 4 + 1], scale_log2, -l2.y));
-          pr[c4 * 4 + 2] = ex2(fmaf(pr[c4 * 4 + 2], scale_log2, -l2.z));
-          pr[c4 * 4 + 3] = ex2(fmaf(pr[c4 * 4 + 3], scale_log2, -l2.w));
+          pr[c4 * 4 + 0] = ex2(fmaf(pr[c4 * 4 + 0], scale_log2, bias2 - l2.x));
+          pr[c4 * 4 + 1] = ex2(fmaf(pr[c4 * 4 + 1], scale_log2, bias2 - l2.y));
+          pr[c4 * 4 + 2] = ex2(fmaf(pr[c4 * 4 + 2], scale_log2, bias2 - l2.z));
+          pr[c4 * 4 + 3] = ex2(fmaf(pr[c4 * 4 + 3], scale_log2, bias2 - l2.w));
         }
       }
       if (!key_valid) {
@@ -655,6 +636,15 @@ extern "C" int ba_bwd_chunk(ba_tensor4 d_o, ba_tensor4 q, ba_tensor4 k, ba_tenso
                             ba_rowstat lse, ba_tensor4 dq_acc, ba_tensor4 dk_acc, ba_tensor4 dv_acc, int B, int Sq,
                             int Sk, int H, int D, float scale, int mask_mode, int causal_offset, int flags, int dtype,
                             void* stream) {
+  ba_rowstat none = {nullptr, 0, 0};
+  return ba_bwd_chunk_bias(d_o, q, k, v, delta, lse, none, dq_acc, dk_acc, dv_acc, B, Sq, Sk, H, D, scale, mask_mode,
+                           causal_offset, flags, dtype, stream);
+}
+
+extern "C" int ba_bwd_chunk_bias(ba_tensor4 d_o, ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_rowstat delta,
+                                 ba_rowstat lse, ba_rowstat key_bias, ba_tensor4 dq_acc, ba_tensor4 dk_acc,
+                                 ba_tensor4 dv_acc, int B, int Sq, int Sk, int H, int D, float scale, int mask_mode,
+                                 int causal_offset, int flags, int dtype, void* stream) {
   using namespace ba;
   BA_REQUIRE(D == 128 || D == 64, "ba_bwd_chunk: head dim %d unsupported (64 or 128)", D);
   BA_REQUIRE(B > 0 && Sq > 0 && Sk > 0 && H > 0, "ba_bwd_chunk: empty problem B=%d Sq=%d Sk=%d H=%d", B, Sq, Sk, H);
@@ -683,6 +673,7 @@ extern "C" int ba_bwd_chunk(ba_tensor4 d_o, ba_tensor4 q, ba_tensor4 k, ba_tenso
   p.dk_sb = dk_acc.stride_b, p.dk_ss = dk_acc.stride_s, p.dk_sh = dk_acc.stride_h;
   p.dv_acc = static_cast<float*>(dv_acc.ptr);
   p.dv_sb = dv_acc.stride_b, p.dv_ss = dv_acc.stride_s, p.dv_sh = dv_acc.stride_h;
+  p.bias = key_bias.ptr, p.bias_sb = key_bias.stride_b, p.bias_sh = key_bias.stride_h;
   p.B = B, p.Sq = Sq, p.Sk = Sk, p.H = H;
   p.scale = scale;
   p.scale_log2 = scale * kBwdLog2e;

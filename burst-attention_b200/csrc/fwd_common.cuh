@@ -25,6 +25,9 @@ struct FwdParams {
   int64_t oout_sb, oout_ss, oout_sh;
   int B, Sq, Sk, H;
   float scale_log2;
+  const float* bias;  // optional additive bias per key [B|1, H, Sk] (fp32), or null
+  int64_t bias_sb, bias_sh;
+  float inv_scale;
   int causal;
   int causal_off;
   int load_state;

@@ -31,6 +31,7 @@ namespace ba {
 struct __align__(8) FwdBarriers {
   uint64_t q_full;
   uint64_t k_full[kKStages], k_empty[kKStages];
+  uint64_t b_full[kKStages];  // kBias: the key-bias operand tile of this K stage has been written
   uint64_t v_full[kVStages], v_empty[kVStages];
   uint64_t s_full[2][2];   // MMA -> softmax: S_w sub-tile buffer b ready in TMEM
   uint64_t p_ready[2][2];  // softmax -> MMA: P_w (buffer b) written (and O_w rescaled)
@@ -51,14 +52,30 @@ struct FwdLayout {
   static constexpr uint32_t kOffQ = 0;
   static constexpr uint32_t kOffK = 2 * kTileB;
   static constexpr uint32_t kOffV = kOffK + kKStages * kTileB;
-  static constexpr uint32_t kOffBars = kOffV + kVStages * kTileB;
+  // kBias: per K stage a [128 keys][16 B] no-swizzle operand tile (bias / scale in three 16-bit parts), and the
+  // constant A operand of the bias K step: [ones core matrix 128 B][zero core matrix 128 B]
+  static constexpr uint32_t kOffBias = kOffV + kVStages * kTileB;
+  static constexpr uint32_t kOffOnes = kOffBias + kKStages * 2048;
+  static constexpr uint32_t kOffBars = kOffOnes + 256;
   static constexpr int kSmemBytes = kOffBars + 256 /*barriers*/;
 };
 
 // One step (sub-tile j, with U = j & 3 known at compile time so that every TMEM address, smem
 // descriptor and barrier address below is a constant): PV for both Q tiles on sub-tile j, then the
 // QK^T of sub-tile j+2 into the S buffers that PV just released.  sb16 = (smem base address) >> 4.
-template <bool kBF16, int kD, int U>
+// S_w (+)= 1[q] (x) (bias[key] / scale): one extra K = 16 step (sm100_ptx.cuh, "fold"); A = one core matrix of
+// identical rows [1 1 1 0 ...] shared by all row groups (SBO = 0) + a zero core matrix for k = 8..15, B = the
+// stage's bias tile, 64 keys of it (second K chunk re-reads the first, LBO = 0: A is zero there)
+template <bool kBF16, int kD>
+__device__ __forceinline__ void fwd_issue_bias(uint32_t sb16, uint32_t tS, int stage, int sub) {
+  using L = FwdLayout<kD>;
+  constexpr uint32_t idesc_qk = make_idesc(kBF16, kBlockM, kSub, false, false);
+  const uint32_t a_lo = sb16 + (L::kOffOnes >> 4) + desc_lo_lbo(128);
+  const uint32_t b_lo = sb16 + ((L::kOffBias + stage * 2048 + sub * 1024) >> 4) + desc_lo_lbo(0);
+  umma_ss_lh(tS, a_lo, desc_hi_noswz(0), b_lo, desc_hi_noswz(128), idesc_qk, 1u);
+}
+
+template <bool kBF16, int kD, bool kBias, int U>
 __device__ __forceinline__ void fwd_mma_step(int j, uint32_t sb16, FwdBarriers* bars, int n_s0, int n_s1, int n_sub,
                                              bool load_state) {
   using L = FwdLayout<kD>;
@@ -93,6 +110,7 @@ __device__ __forceinline__ void fwd_mma_step(int j, uint32_t sb16, FwdBarriers* 
     if (next_qk) {
       if (w == 0 && sub == 0) {
         mbar_wait(&bars->k_full[st_next], ((tile + 1) >> 1) & 1);
+        if constexpr (kBias) mbar_wait(&bars->b_full[st_next], ((tile + 1) >> 1) & 1);
         tc_fence_after();
       }
       if (j + 2 < n_w) {
@@ -104,6 +122,7 @@ __device__ __forceinline__ void fwd_mma_step(int j, uint32_t sb16, FwdBarriers* 
           const uint32_t off = ((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4;
           umma_ss_lh(tS, a_lo + off, hi, k_lo + off, hi, idesc_qk, kk > 0 ? 1u : 0u);
         }
+        if constexpr (kBias) fwd_issue_bias<kBF16, kD>(sb16, tS, st_next, sub);
         umma_commit(&bars->s_full[w][sub]);
       }
       if (w == 1 && sub == 1) umma_commit(&bars->k_empty[st_next]);
@@ -119,7 +138,7 @@ __device__ __forceinline__ int fwd_trip_count(int r0, const FwdParams& p) {
   return max_limit < 0 ? 0 : max_limit / kSub + 1;
 }
 
-template <bool kBF16, int kD>
+template <bool kBF16, int kD, bool kBias>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
@@ -156,6 +175,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int i = 0; i < kKStages; ++i) {
         mbar_init(&bars->k_full[i], 1);
         mbar_init(&bars->k_empty[i], 1);
+        mbar_init(&bars->b_full[i], 1);
       }
       for (int i = 0; i < kVStages; ++i) {
         mbar_init(&bars->v_full[i], 1);
@@ -170,6 +190,12 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_init(&bars->o_final[w], 1);
       }
       fence_mbar_init();
+    }
+    if (kBias && lane < 16) {  // constant A operand of the bias K step: ones in slots 0..2 | zero core matrix
+      constexpr uint32_t one = kBF16 ? 0x3F80u : 0x3C00u;
+      *reinterpret_cast<uint4*>(smem + L::kOffOnes + lane * 16) =
+          lane < 8 ? make_uint4(one | (one << 16), one, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+      fence_proxy_async_smem();
     }
     __syncwarp();
     tmem_alloc(&bars->tmem_base, 512);
@@ -191,13 +217,34 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int half = 0; half < kBoxes; ++half)
           tma_load_4d(sQ + w * kTileBytes + half * kBoxBytes, &tmQ, &bars->q_full, half * 64, h,
                       row0 + w * kBlockM, b);
-      for (int i = 0; i < n_tiles; ++i) {
-        const int ks = i % kKStages, kph = (i / kKStages) & 1;
-        mbar_wait(&bars->k_empty[ks], kph ^ 1);
+    }
+    for (int i = 0; i < n_tiles; ++i) {
+      const int ks = i % kKStages, kph = (i / kKStages) & 1;
+      if (kBias || lane == 0) mbar_wait(&bars->k_empty[ks], kph ^ 1);
+      if (lane == 0) {
         mbar_arrive_expect_tx(&bars->k_full[ks], kTileBytes);
         for (int half = 0; half < kBoxes; ++half)
           tma_load_4d(sK + ks * kTileBytes + half * kBoxBytes, &tmK, &bars->k_full[ks], half * 64, h,
                       i * kBlockN, b);
+      }
+      if constexpr (kBias) {  // the stage's key-bias operand tile: lane handles keys lane + 32 j
+        constexpr float kBig = kBF16 ? 1e30f : 60000.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = lane + 32 * j, key = i * kBlockN + r;
+          float x = 0.f;
+          if (key < p.Sk) x = __ldg(p.bias + (int64_t)b * p.bias_sb + (int64_t)h * p.bias_sh + key) * p.inv_scale;
+          x = fminf(fmaxf(x, -kBig), kBig);
+          uint32_t h0, h1, h2;
+          split3<kBF16>(x, h0, h1, h2);
+          *reinterpret_cast<uint4*>(smem + L::kOffBias + ks * 2048 + (r >> 3) * 128 + (r & 7) * 16) =
+              make_uint4(h0 | (h1 << 16), h2, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->b_full[ks]);
+      }
+      if (lane == 0) {
         const int vs = i % kVStages, vph = (i / kVStages) & 1;
         mbar_wait(&bars->v_empty[vs], vph ^ 1);
         mbar_arrive_expect_tx(&bars->v_full[vs], kTileBytes);
@@ -205,6 +252,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tma_load_4d(sV + vs * kTileBytes + half * kBoxBytes, &tmV, &bars->v_full[vs], half * 64, h,
                       i * kBlockN, b);
       }
+      __syncwarp();
     }
   } else if (warp == 8) {
     // ============================================================ MMA issuer (whole warp, elected lane issues)
@@ -214,6 +262,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       constexpr uint32_t hi = desc_hi(1024);
       mbar_wait(&bars->q_full, 0);
       mbar_wait(&bars->k_full[0], 0);
+      if constexpr (kBias) mbar_wait(&bars->b_full[0], 0);
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -227,6 +276,7 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               const uint32_t off = ((kk >> 2) * kBoxBytes + (kk & 3) * 32) >> 4;
               umma_ss_lh(w * 128 + j * kSub, a_lo + off, hi, k_lo + off, hi, idesc_qk, kk > 0 ? 1u : 0u);
             }
+            if constexpr (kBias) fwd_issue_bias<kBF16, kD>(sb16, w * 128 + j * kSub, 0, j);
             umma_commit(&bars->s_full[w][j]);
           }
         }
@@ -235,10 +285,10 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     const bool ls = p.load_state != 0;
     for (int j0 = 0; j0 < n_sub; j0 += 4) {
-      fwd_mma_step<kBF16, kD, 0>(j0, sb16, bars, n_s0, n_s1, n_sub, ls);
-      if (j0 + 1 < n_sub) fwd_mma_step<kBF16, kD, 1>(j0 + 1, sb16, bars, n_s0, n_s1, n_sub, ls);
-      if (j0 + 2 < n_sub) fwd_mma_step<kBF16, kD, 2>(j0 + 2, sb16, bars, n_s0, n_s1, n_sub, ls);
-      if (j0 + 3 < n_sub) fwd_mma_step<kBF16, kD, 3>(j0 + 3, sb16, bars, n_s0, n_s1, n_sub, ls);
+      fwd_mma_step<kBF16, kD, kBias, 0>(j0, sb16, bars, n_s0, n_s1, n_sub, ls);
+      if (j0 + 1 < n_sub) fwd_mma_step<kBF16, kD, kBias, 1>(j0 + 1, sb16, bars, n_s0, n_s1, n_sub, ls);
+      if (j0 + 2 < n_sub) fwd_mma_step<kBF16, kD, kBias, 2>(j0 + 2, sb16, bars, n_s0, n_s1, n_sub, ls);
+      if (j0 + 3 < n_sub) fwd_mma_step<kBF16, kD, kBias, 3>(j0 + 3, sb16, bars, n_s0, n_s1, n_sub, ls);
     }
   } else {
     // ============================================================ softmax warps
@@ -414,10 +464,10 @@ fwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 
-template <bool kBF16, int kD>
+template <bool kBF16, int kD, bool kBias>
 static int launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const FwdParams& p,
                       cudaStream_t stream) {
-  auto kern = fwd_chunk_kernel<kBF16, kD>;
+  auto kern = fwd_chunk_kernel<kBF16, kD, kBias>;
   constexpr int smem = FwdLayout<kD>::kSmemBytes;
   BA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((p.Sq + 2 * kBlockM - 1) / (2 * kBlockM), p.H, p.B);
@@ -428,9 +478,24 @@ static int launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUte
 
 }  // namespace ba
 
+template <int kD, bool kBias>
+static int launch_fwd_dt(int dtype, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                         const ba::FwdParams& p, cudaStream_t st) {
+  return dtype == BA_DTYPE_BF16 ? ba::launch_fwd<true, kD, kBias>(tmQ, tmK, tmV, p, st)
+                                : ba::launch_fwd<false, kD, kBias>(tmQ, tmK, tmV, p, st);
+}
+
 extern "C" int ba_fwd_chunk(ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_tensor4 o_acc, ba_rowstat lse,
                             ba_tensor4 o_out, int B, int Sq, int Sk, int H, int D, float scale, int mask_mode,
                             int causal_offset, int flags, int dtype, void* stream) {
+  ba_rowstat none = {nullptr, 0, 0};
+  return ba_fwd_chunk_bias(q, k, v, none, o_acc, lse, o_out, B, Sq, Sk, H, D, scale, mask_mode, causal_offset, flags,
+                           dtype, stream);
+}
+
+extern "C" int ba_fwd_chunk_bias(ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_rowstat key_bias, ba_tensor4 o_acc,
+                                 ba_rowstat lse, ba_tensor4 o_out, int B, int Sq, int Sk, int H, int D, float scale,
+                                 int mask_mode, int causal_offset, int flags, int dtype, void* stream) {
   using namespace ba;
   BA_REQUIRE(D == 128 || D == 64, "ba_fwd_chunk: head dim %d unsupported (64 or 128)", D);
   BA_REQUIRE(B > 0 && Sq > 0 && Sk > 0 && H > 0, "ba_fwd_chunk: empty problem B=%d Sq=%d Sk=%d H=%d", B, Sq, Sk, H);
@@ -472,7 +537,9 @@ extern "C" int ba_fwd_chunk(ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_tensor4
   p.load_state = first ? 0 : 1;
   p.store_lowp = last ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (D == 64)
-    return dtype == BA_DTYPE_BF16 ? launch_fwd<true, 64>(tmQ, tmK, tmV, p, st) : launch_fwd<false, 64>(tmQ, tmK, tmV, p, st);
-  return dtype == BA_DTYPE_BF16 ? launch_fwd<true, 128>(tmQ, tmK, tmV, p, st) : launch_fwd<false, 128>(tmQ, tmK, tmV, p, st);
+  p.bias = key_bias.ptr, p.bias_sb = key_bias.stride_b, p.bias_sh = key_bias.stride_h;
+  p.inv_scale = 1.f / scale;
+  if (key_bias.ptr)
+    return D == 64 ? launch_fwd_dt<64, true>(dtype, tmQ, tmK, tmV, p, st) : launch_fwd_dt<128, true>(dtype, tmQ, tmK, tmV, p, st);
+  return D == 64 ? launch_fwd_dt<64, false>(dtype, tmQ, tmK, tmV, p, st) : launch_fwd_dt<128, false>(dtype, tmQ, tmK, tmV, p, st);
 }

@@ -408,6 +408,40 @@ BA_DEVICE void umma_commit_2cta(uint64_t* bar, uint16_t cta_mask) {
       : "memory");
 }
 
+// ------------------------------------------------------------------ no-swizzle K-major operands, fp32 -> 3 x 16 bit
+// K-major, NO swizzle: core matrix = 8 rows x 16 B stored contiguously (128 B); LBO = byte distance between the
+// two core matrices of one K = 16 step, SBO = byte distance between 8-row groups.  Used for the rank-1 "fold"
+// K steps that add a per-row / per-column fp32 vector to an accumulator on the tensor core: the vector is split
+// into three 16-bit parts (hi + lo + lolo, exact to fp32 round-off) that multiply 1.0.
+BA_DEVICE uint64_t make_smem_desc_noswz(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell); swizzle field = 0: none
+  return d;
+}
+template <bool kBF16>
+BA_DEVICE uint32_t to16(float x) {
+  if constexpr (kBF16) return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+  else return __half_as_ushort(__float2half_rn(x));
+}
+template <bool kBF16>
+BA_DEVICE float from16(uint32_t h) {
+  if constexpr (kBF16) return __bfloat162float(__ushort_as_bfloat16(static_cast<unsigned short>(h)));
+  else return __half2float(__ushort_as_half(static_cast<unsigned short>(h)));
+}
+template <bool kBF16>
+BA_DEVICE void split3(float x, uint32_t& h0, uint32_t& h1, uint32_t& h2) {
+  h0 = to16<kBF16>(x);
+  float r = x - from16<kBF16>(h0);
+  h1 = to16<kBF16>(r);
+  r -= from16<kBF16>(h1);
+  h2 = to16<kBF16>(r);
+}
+
+__host__ __device__ constexpr uint32_t desc_hi_noswz(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14); }
+
 // ------------------------------------------------------------------ packing
 template <bool kBF16>
 BA_DEVICE uint32_t pack2(float lo, float hi) {

@@ -74,10 +74,20 @@ int ba_version(void);
  * running state (o_acc fp32, already normalised; lse fp32 [B,H,Sq]).
  *   flags & BA_FWD_FIRST : state is not read.
  *   flags & BA_FWD_LAST  : o_out (dtype) is written instead of o_acc; lse is always written.
- * D must be 128; Sq, Sk arbitrary (>0).  scale > 0.                              */
+ * D must be 64 or 128; Sq, Sk arbitrary (>0).  scale > 0.                        */
 int ba_fwd_chunk(ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_tensor4 o_acc, ba_rowstat lse, ba_tensor4 o_out,
                  int B, int Sq, int Sk, int H, int D, float scale, int mask_mode, int causal_offset, int flags,
                  int dtype, void* stream);
+
+/* The same with an additive attention bias per KEY: scores = q k^T * scale + key_bias[b,h,key]  (the "vector" bias
+ * of the reference's LAO tile, burst_attn/lao.py:102-105,155-173; its ring op always passes bias = None,
+ * burst_attn_interface.py:223,316, so this serves the single-GPU wrappers of burst_attn/flash_triton.py).
+ * key_bias: fp32 [B,H,Sk] view (stride_b may be 0 to broadcast over the batch; ptr NULL = no bias).  -inf entries
+ * mask a key.  The forward adds it on the tensor core (one extra K = 16 step per score tile), the backward in the
+ * exponent's FMA; no gradient is produced for the bias (neither does the reference: flash_triton.py:1046).       */
+int ba_fwd_chunk_bias(ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_rowstat key_bias, ba_tensor4 o_acc, ba_rowstat lse,
+                      ba_tensor4 o_out, int B, int Sq, int Sk, int H, int D, float scale, int mask_mode,
+                      int causal_offset, int flags, int dtype, void* stream);
 
 /* delta[b,h,s] = sum_d O[b,s,h,d] * dO[b,s,h,d]  (burst_attn_interface.py:272-278) */
 int ba_bwd_delta(ba_tensor4 o, ba_tensor4 d_o, ba_rowstat delta, int B, int S, int H, int D, int dtype,
@@ -92,6 +102,10 @@ int ba_bwd_delta(ba_tensor4 o, ba_tensor4 d_o, ba_rowstat delta, int B, int S, i
 int ba_bwd_chunk(ba_tensor4 d_o, ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_rowstat delta, ba_rowstat lse,
                  ba_tensor4 dq_acc, ba_tensor4 dk_acc, ba_tensor4 dv_acc, int B, int Sq, int Sk, int H, int D,
                  float scale, int mask_mode, int causal_offset, int flags, int dtype, void* stream);
+
+int ba_bwd_chunk_bias(ba_tensor4 d_o, ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_rowstat delta, ba_rowstat lse,
+                      ba_rowstat key_bias, ba_tensor4 dq_acc, ba_tensor4 dk_acc, ba_tensor4 dv_acc, int B, int Sq, int Sk,
+                      int H, int D, float scale, int mask_mode, int causal_offset, int flags, int dtype, void* stream);
 
 /* dst[b,s,h,d] (dtype) = src[b,s,h,d] (fp32); used once per backward to hand the
  * fp32 gradient accumulators back in the input dtype.                              */

@@ -29,15 +29,19 @@ NEG_INF = float("-inf")
 # dense reference (what the reference's own test compares against:
 # test/test_burst.py:175,184 runs flash_attn_func on the full sequence)
 # --------------------------------------------------------------------------- #
-def dense_attention(q, k, v, scale=None, causal=False, dtype=torch.float64):
-    """softmax(q k^T * scale [+ causal mask]) v on the full sequence.
+def dense_attention(q, k, v, scale=None, causal=False, dtype=torch.float64, bias=None):
+    """softmax(q k^T * scale [+ bias] [+ causal mask]) v on the full sequence.
 
-    q,k,v: [B,S,H,D].  Returns (o [B,S,H,D], lse [B,H,S]) in ``dtype``.
+    q,k,v: [B,S,H,D].  bias: optional additive bias broadcastable to [B,H,Sq,Sk], added after the scale exactly
+    as the reference's LAO tile does (``qk = qk * softmax_scale + bias``, lao.py:155-173).
+    Returns (o [B,S,H,D], lse [B,H,S]) in ``dtype``.
     """
     q, k, v = (t.to(dtype) for t in (q, k, v))
     if scale is None:
         scale = 1.0 / math.sqrt(q.shape[-1])
     s = torch.einsum("bqhd,bkhd->bhqk", q, k) * scale
+    if bias is not None:
+        s = s + bias.to(dtype)
     if causal:
         sq, sk = s.shape[-2:]
         mask = torch.ones(sq, sk, dtype=torch.bool).tril(diagonal=sk - sq)
@@ -48,13 +52,15 @@ def dense_attention(q, k, v, scale=None, causal=False, dtype=torch.float64):
     return o, lse
 
 
-def dense_attention_bwd(q, k, v, do, scale=None, causal=False, dtype=torch.float64):
+def dense_attention_bwd(q, k, v, do, scale=None, causal=False, dtype=torch.float64, bias=None):
     """Analytic gradients of dense_attention (same math autograd would do)."""
     q, k, v, do = (t.to(dtype) for t in (q, k, v, do))
     if scale is None:
         scale = 1.0 / math.sqrt(q.shape[-1])
-    o, lse = dense_attention(q, k, v, scale, causal, dtype)
+    o, lse = dense_attention(q, k, v, scale, causal, dtype, bias)
     s = torch.einsum("bqhd,bkhd->bhqk", q, k) * scale
+    if bias is not None:
+        s = s + bias.to(dtype)
     p = torch.exp(s - lse.unsqueeze(-1))
     if causal:
         sq, sk = s.shape[-2:]

@@ -96,3 +96,30 @@ def test_packed_qkv_wrappers_match_oracle(causal):
     torch.testing.assert_close(o.double().cpu(), o_ref, **TOL[dtype])
     with pytest.raises(NotImplementedError):
         flash_attn_func(qq, kk, vv, torch.zeros(1, n, s, s, device="cuda"), causal)
+
+
+@pytest.mark.parametrize("D", [128, 64])
+@pytest.mark.parametrize("causal", [False, True])
+def test_key_vector_bias(monkeypatch, D, causal):
+    """The "vector" bias of the reference's LAO tile (lao.py:102-105,155-173): scores = q k^T * scale + bias[b,h,key],
+    incl. -inf entries (key-padding mask) and a batch-broadcast bias, through L2-blocked sub-launches."""
+    from burst_attn.flash_triton import flash_attn_func
+    monkeypatch.setenv("BA_L2_BLOCK", "256")
+    torch.manual_seed(6)
+    dtype = torch.bfloat16
+    b, s, n = 2, 700, 3
+    q, k, v, do = (torch.randn(b, s, n, D, device="cuda", dtype=dtype) for _ in range(4))
+    for bias in (torch.randn(b, n, 1, s, device="cuda") * 2.0, torch.randn(1, n, 1, s, device="cuda")):
+        bias[:, :, :, 5::7] = float("-inf")  # masked keys
+        bias[:, 0, :, 1] = 30.0              # one dominant key
+        qq, kk, vv = (t.clone().requires_grad_() for t in (q, k, v))
+        o = flash_attn_func(qq, kk, vv, bias, causal)
+        dq, dk, dv = torch.autograd.grad(o, (qq, kk, vv), do)
+        o_ref, _, dq_ref, dk_ref, dv_ref = orc.dense_attention_bwd(q.cpu(), k.cpu(), v.cpu(), do.cpu(), None, causal,
+                                                                   bias=bias.cpu())
+        if causal:  # row 0 sees only key 0 (finite bias); rows whose visible keys are all masked do not exist here
+            assert not torch.isnan(o_ref).any()
+        for got, ref in ((o, o_ref), (dq, dq_ref), (dk, dk_ref), (dv, dv_ref)):
+            assert not torch.isnan(got).any()
+            torch.testing.assert_close(got.double().cpu(), ref, **TOL[dtype])
+        assert torch.all(dk[:, 5::7] == 0) and torch.all(dv[:, 5::7] == 0)  # masked keys get no gradient

@@ -30,6 +30,11 @@ fi
 CFG="65536,524288c"; [ "$N" -ge 8 ] && CFG="65536,524288c,1048576"
 run timeout 400 $TR --master-port $(port) bench.py --gpus $N --steps 3 --warmup 3 --ab-comm > gpurun_out/bench_${TAG}_n${N}_nccl.json 2> gpurun_out/bench_${TAG}_n${N}_nccl.err
 run timeout 500 $TR --master-port $(port) bench.py --gpus $N --steps 2 --warmup 3 --ab-comm --no-e2e --no-parity --configs $CFG > gpurun_out/bench_${TAG}_n${N}_nccl_cfg.json 2> gpurun_out/bench_${TAG}_n${N}_nccl_cfg.err
+# 4b. NCCL's send/recv kernels are SM-resident and slow the tile kernels down while they co-run (round 1: fwd +8.7 %
+#     at N = 8); the ring needs < 100 GB/s per hop, so cap the CTAs NCCL may use
+for c in 2 4; do
+  NCCL_MAX_CTAS=$c run timeout 300 $TR --master-port $(port) bench.py --gpus $N --steps 3 --warmup 3 --no-e2e --no-parity > gpurun_out/bench_${TAG}_n${N}_ncclcta${c}.json 2> gpurun_out/bench_${TAG}_n${N}_ncclcta${c}.err
+done
 # 5. the same over the copy engines
 if [ "$CE_OK" = 1 ]; then
   BA_RING_TRANSPORT=ce run timeout 400 $TR --master-port $(port) bench.py --gpus $N --steps 3 --warmup 3 --no-e2e --configs 262144,65536 > gpurun_out/bench_${TAG}_n${N}_ce.json 2> gpurun_out/bench_${TAG}_n${N}_ce.err
