@@ -5,6 +5,7 @@
 # Everything is wrapped in `timeout`: a transport that hangs costs its own limit, not the session.
 N=${1:-2}; TAG=${2:-r02}
 mkdir -p gpurun_out
+python -c "import torch; print(torch.cuda.device_count(), torch.cuda.get_device_name(0))"  # pages the image in (can take minutes on a cold box)
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 port() { echo $((29500 + RANDOM % 400)); }
 run() { echo "=== $*"; "$@"; echo "--- rc=$?"; }
@@ -27,12 +28,12 @@ if [ "$N" -ge 8 ]; then
 fi
 
 # 4. bench: flat ring over NCCL (headline config first, with e2e and the comm A/B), then the other configurations
-CFG="65536,524288c"; [ "$N" -ge 8 ] && CFG="65536,524288c,1048576"
+CFG="65536,524288c"; [ "$N" -ge 8 ] && [ "${FULL:-0}" = 1 ] && CFG="65536,524288c,1048576"
 run timeout 400 $TR --master-port $(port) bench.py --gpus $N --steps 3 --warmup 3 --ab-comm > gpurun_out/bench_${TAG}_n${N}_nccl.json 2> gpurun_out/bench_${TAG}_n${N}_nccl.err
 run timeout 500 $TR --master-port $(port) bench.py --gpus $N --steps 2 --warmup 3 --ab-comm --no-e2e --no-parity --configs $CFG > gpurun_out/bench_${TAG}_n${N}_nccl_cfg.json 2> gpurun_out/bench_${TAG}_n${N}_nccl_cfg.err
 # 4b. NCCL's send/recv kernels are SM-resident and slow the tile kernels down while they co-run (round 1: fwd +8.7 %
 #     at N = 8); the ring needs < 100 GB/s per hop, so cap the CTAs NCCL may use
-for c in 2 4; do
+for c in ${NCCL_CTAS:-2 4}; do
   NCCL_MAX_CTAS=$c run timeout 300 $TR --master-port $(port) bench.py --gpus $N --steps 3 --warmup 3 --no-e2e --no-parity > gpurun_out/bench_${TAG}_n${N}_ncclcta${c}.json 2> gpurun_out/bench_${TAG}_n${N}_ncclcta${c}.err
 done
 # 5. the same over the copy engines
