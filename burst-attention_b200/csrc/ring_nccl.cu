@@ -8,6 +8,7 @@
 // events; no host synchronisation anywhere.  A ring whose receive arena has been connected
 // (ba_ring_arena_*, ring_ce.cu) posts its hops over the copy engines instead.
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -26,6 +27,7 @@ constexpr int kNcclInt8 = 0;
 struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*);
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, void*);  // optional (NCCL >= 2.14)
   ncclResult_t (*CommDestroy)(ncclComm_t);
   ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t);
@@ -55,10 +57,28 @@ static NcclApi& nccl() {
     BA_SYM(GroupEnd)
     BA_SYM(GetErrorString)
 #undef BA_SYM
+    api.CommInitRankConfig = reinterpret_cast<decltype(api.CommInitRankConfig)>(dlsym(h, "ncclCommInitRankConfig"));
     api.ok = true;
   });
   return api;
 }
+
+// ncclConfig_t as of NCCL 2.18 (newer libraries accept an older, shorter struct by its size/version fields and
+// default the attributes added later).  Only maxCTAs is set: the ring moves a few hundred MB per round while the
+// tile kernels own every SM, and each CTA NCCL's SM-resident send/recv kernel occupies is an SM the tile kernel
+// loses for the duration of the hop -- the hop needs bandwidth for < 100 GB/s, not NCCL's default channel count.
+struct NcclConfigV21800 {
+  size_t size;
+  unsigned int magic;
+  unsigned int version;
+  int blocking;
+  int cgaClusterSize;
+  int minCTAs;
+  int maxCTAs;
+  const char* netName;
+  int splitShare;
+};
+constexpr int kNcclUndefInt = -2147483647 - 1;  // NCCL_CONFIG_UNDEF_INT
 
 static int nccl_fail(ncclResult_t r, const char* what) {
   set_error("NCCL error %d (%s) at %s", r, nccl().ok ? nccl().GetErrorString(r) : "?", what);
@@ -104,7 +124,16 @@ extern "C" int ba_ring_create(const void* id128, int rank, int world, ba_ring** 
     }
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
-    BA_CHECK_NCCL(nccl().CommInitRank(&r->comm, world, id, rank));
+    // BA_NCCL_MAX_CTAS (default 0 = NCCL's own choice): cap the CTAs of this ring's send/recv kernels
+    const char* e = getenv("BA_NCCL_MAX_CTAS");
+    const int max_ctas = e ? atoi(e) : 0;
+    if (max_ctas > 0 && nccl().CommInitRankConfig) {
+      NcclConfigV21800 cfg = {sizeof(NcclConfigV21800), 0xcafebeefu, 21800u, kNcclUndefInt, kNcclUndefInt, 1, max_ctas,
+                              nullptr, kNcclUndefInt};
+      BA_CHECK_NCCL(nccl().CommInitRankConfig(&r->comm, world, id, rank, &cfg));
+    } else {
+      BA_CHECK_NCCL(nccl().CommInitRank(&r->comm, world, id, rank));
+    }
   }
   *out = r;
   return BA_OK;

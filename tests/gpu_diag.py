@@ -99,7 +99,7 @@ def perf_stage():
     for causal in (False, True):
         f = lambda: ops.fwd_chunk(q, k, v, None, lse, out, 128 ** -0.5, causal, 0, True, True, 1)
         ms = t(f)
-        say(f"[perf fwd causal={causal} poly={os.environ.get('BA_FWD_POLY', '0')}] ms={ms:.3f} "
+        say(f"[perf fwd causal={causal}] ms={ms:.3f} "
             f"tflops={4 * S * S * H * 128 / (2 if causal else 1) / ms / 1e9:.1f}")
     for causal in (False, True):
         f = lambda: ops.bwd_chunk(do, q, k, v, delta, lse, acc[0], acc[1], acc[2], 128 ** -0.5, causal, 0, 1)

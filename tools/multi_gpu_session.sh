@@ -34,7 +34,7 @@ run timeout 500 $TR --master-port $(port) bench.py --gpus $N --steps 2 --warmup 
 # 4b. NCCL's send/recv kernels are SM-resident and slow the tile kernels down while they co-run (round 1: fwd +8.7 %
 #     at N = 8); the ring needs < 100 GB/s per hop, so cap the CTAs NCCL may use
 for c in ${NCCL_CTAS:-2 4}; do
-  NCCL_MAX_CTAS=$c run timeout 300 $TR --master-port $(port) bench.py --gpus $N --steps 3 --warmup 3 --no-e2e --no-parity > gpurun_out/bench_${TAG}_n${N}_ncclcta${c}.json 2> gpurun_out/bench_${TAG}_n${N}_ncclcta${c}.err
+  BA_NCCL_MAX_CTAS=$c run timeout 300 $TR --master-port $(port) bench.py --gpus $N --steps 3 --warmup 3 --no-e2e --no-parity > gpurun_out/bench_${TAG}_n${N}_ncclcta${c}.json 2> gpurun_out/bench_${TAG}_n${N}_ncclcta${c}.err
 done
 # 5. the same over the copy engines
 if [ "$CE_OK" = 1 ]; then
