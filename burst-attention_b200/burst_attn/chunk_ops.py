@@ -35,7 +35,8 @@ class NativeOps:
     def enable_timing(self, on=True):
         """Bracket every launch with CUDA events on the launching stream (bench.py roofline)."""
         self.timing = {} if on else None
-        self.shapes = {}  # {kernel name: {(Sq, Sk, H, causal): launches}} while timing is on
+        if on:
+            self.shapes = {}  # {kernel name: {(Sq, Sk, H, causal): launches}} since timing was switched on
 
     def _t0(self, dev):
         if self.timing is None:

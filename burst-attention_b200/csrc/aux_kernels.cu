@@ -1,22 +1,22 @@
 // HBM-bound helpers around the tile kernels: delta = rowsum(O*dO), fp32 -> 16-bit
 // cast of the gradient accumulators, and fp32 accumulate (dQ add-on-arrival).
-// All are one pass over their operands with 16-byte accesses; D = 128 so one
-// warp covers four (row, head) pairs per instruction step.
+// All are one pass over their operands with 16-byte accesses; head dim D = 64 or 128: a (row, head) pair is
+// covered by D/16 (delta), D/8 (cast) or D/4 (accumulate) consecutive threads (`lpr`, a power of two).
 #include "host_common.h"
 #include "sm100_ptx.cuh"
 
 namespace ba {
 
 // delta[b,h,s] = sum_d O[b,s,h,d] * dO[b,s,h,d]     (burst_attn_interface.py:272-278)
-// 8 lanes x 16 elements cover one 128-wide row; a warp handles 4 consecutive heads.
+// D/16 lanes x 16 elements cover one row; a warp handles 32 / (D/16) consecutive (row, head) pairs.
 template <bool kBF16>
 __global__ void __launch_bounds__(256)
 delta_kernel(const uint16_t* __restrict__ o, int64_t o_sb, int64_t o_ss, int64_t o_sh,
              const uint16_t* __restrict__ d_o, int64_t do_sb, int64_t do_ss, int64_t do_sh,
-             float* __restrict__ delta, int64_t dl_sb, int64_t dl_sh, int B, int S, int H) {
+             float* __restrict__ delta, int64_t dl_sb, int64_t dl_sh, int B, int S, int H, int lpr_log2) {
   const int64_t total = (int64_t)B * S * H;  // (b, s, h) rows, h fastest
-  const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  const int sub = threadIdx.x & 7;
+  const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> lpr_log2;
+  const int sub = threadIdx.x & ((1 << lpr_log2) - 1);
   float acc = 0.f;
   int b = 0, s = 0, h = 0;
   const bool valid = gid < total;
@@ -48,7 +48,7 @@ delta_kernel(const uint16_t* __restrict__ o, int64_t o_sb, int64_t o_ss, int64_t
   }
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
   acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (lpr_log2 == 3) acc += __shfl_xor_sync(0xffffffffu, acc, 4);
   if (valid && sub == 0) delta[b * dl_sb + h * dl_sh + s] = acc;
 }
 
@@ -56,12 +56,12 @@ delta_kernel(const uint16_t* __restrict__ o, int64_t o_sb, int64_t o_ss, int64_t
 template <bool kBF16>
 __global__ void __launch_bounds__(256)
 cast_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_ss, int64_t s_sh, uint16_t* __restrict__ dst,
-            int64_t d_sb, int64_t d_ss, int64_t d_sh, int B, int S, int H) {
-  const int64_t total = (int64_t)B * S * H * 16;  // 16 threads per 128-wide row
+            int64_t d_sb, int64_t d_ss, int64_t d_sh, int B, int S, int H, int lpr_log2) {
+  const int64_t total = ((int64_t)B * S * H) << lpr_log2;  // D/8 threads per row
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
-  const int sub = gid & 15;
-  const int64_t r = gid >> 4;
+  const int sub = gid & ((1 << lpr_log2) - 1);
+  const int64_t r = gid >> lpr_log2;
   const int h = r % H;
   const int64_t bs = r / H;
   const int s = bs % S;
@@ -79,12 +79,12 @@ cast_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_ss, int64_t s
 // dst(fp32) += src(fp32), 4 elements per thread
 __global__ void __launch_bounds__(256)
 accumulate_kernel(const float* __restrict__ src, int64_t s_sb, int64_t s_ss, int64_t s_sh, float* __restrict__ dst,
-                  int64_t d_sb, int64_t d_ss, int64_t d_sh, int B, int S, int H) {
-  const int64_t total = (int64_t)B * S * H * 32;  // 32 threads per 128-wide row
+                  int64_t d_sb, int64_t d_ss, int64_t d_sh, int B, int S, int H, int lpr_log2) {
+  const int64_t total = ((int64_t)B * S * H) << lpr_log2;  // D/4 threads per row
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
-  const int sub = gid & 31;
-  const int64_t r = gid >> 5;
+  const int sub = gid & ((1 << lpr_log2) - 1);
+  const int64_t r = gid >> lpr_log2;
   const int h = r % H;
   const int64_t bs = r / H;
   const int s = bs % S;
@@ -107,22 +107,23 @@ static bool aligned16(const ba_tensor4& t, int esize) {
 extern "C" int ba_bwd_delta(ba_tensor4 o, ba_tensor4 d_o, ba_rowstat delta, int B, int S, int H, int D, int dtype,
                             void* stream) {
   using namespace ba;
-  BA_REQUIRE(D == 128, "ba_bwd_delta: head dim %d unsupported (only 128)", D);
+  BA_REQUIRE(D == 128 || D == 64, "ba_bwd_delta: head dim %d unsupported (64 or 128)", D);
+  const int lpr_log2 = D == 128 ? 3 : 2;
   BA_REQUIRE(B > 0 && S > 0 && H > 0, "ba_bwd_delta: empty problem");
   BA_REQUIRE(o.ptr && d_o.ptr && delta.ptr, "ba_bwd_delta: null pointer");
   BA_REQUIRE(aligned16(o, 2) && aligned16(d_o, 2), "ba_bwd_delta: o/dO must be 16-byte aligned views");
   const int64_t rows = (int64_t)B * S * H;
-  const int64_t threads = rows * 8;
+  const int64_t threads = rows << lpr_log2;
   const unsigned blocks = (unsigned)((threads + 255) / 256);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == BA_DTYPE_BF16)
     delta_kernel<true><<<blocks, 256, 0, st>>>((const uint16_t*)o.ptr, o.stride_b, o.stride_s, o.stride_h,
                                                (const uint16_t*)d_o.ptr, d_o.stride_b, d_o.stride_s, d_o.stride_h,
-                                               delta.ptr, delta.stride_b, delta.stride_h, B, S, H);
+                                               delta.ptr, delta.stride_b, delta.stride_h, B, S, H, lpr_log2);
   else
     delta_kernel<false><<<blocks, 256, 0, st>>>((const uint16_t*)o.ptr, o.stride_b, o.stride_s, o.stride_h,
                                                 (const uint16_t*)d_o.ptr, d_o.stride_b, d_o.stride_s, d_o.stride_h,
-                                                delta.ptr, delta.stride_b, delta.stride_h, B, S, H);
+                                                delta.ptr, delta.stride_b, delta.stride_h, B, S, H, lpr_log2);
   BA_CHECK_CUDA(cudaGetLastError());
   return BA_OK;
 }
@@ -130,32 +131,34 @@ extern "C" int ba_bwd_delta(ba_tensor4 o, ba_tensor4 d_o, ba_rowstat delta, int 
 extern "C" int ba_cast_from_f32(ba_tensor4 src, ba_tensor4 dst, int B, int S, int H, int D, int dtype,
                                 void* stream) {
   using namespace ba;
-  BA_REQUIRE(D == 128, "ba_cast_from_f32: head dim %d unsupported (only 128)", D);
+  BA_REQUIRE(D == 128 || D == 64, "ba_cast_from_f32: head dim %d unsupported (64 or 128)", D);
+  const int lpr_log2 = D == 128 ? 4 : 3;
   BA_REQUIRE(B > 0 && S > 0 && H > 0 && src.ptr && dst.ptr, "ba_cast_from_f32: bad arguments");
   BA_REQUIRE(aligned16(src, 4) && aligned16(dst, 2), "ba_cast_from_f32: views must be 16-byte aligned");
-  const int64_t threads = (int64_t)B * S * H * 16;
+  const int64_t threads = ((int64_t)B * S * H) << lpr_log2;
   const unsigned blocks = (unsigned)((threads + 255) / 256);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == BA_DTYPE_BF16)
     cast_kernel<true><<<blocks, 256, 0, st>>>((const float*)src.ptr, src.stride_b, src.stride_s, src.stride_h,
-                                              (uint16_t*)dst.ptr, dst.stride_b, dst.stride_s, dst.stride_h, B, S, H);
+                                              (uint16_t*)dst.ptr, dst.stride_b, dst.stride_s, dst.stride_h, B, S, H, lpr_log2);
   else
     cast_kernel<false><<<blocks, 256, 0, st>>>((const float*)src.ptr, src.stride_b, src.stride_s, src.stride_h,
-                                               (uint16_t*)dst.ptr, dst.stride_b, dst.stride_s, dst.stride_h, B, S, H);
+                                               (uint16_t*)dst.ptr, dst.stride_b, dst.stride_s, dst.stride_h, B, S, H, lpr_log2);
   BA_CHECK_CUDA(cudaGetLastError());
   return BA_OK;
 }
 
 extern "C" int ba_accumulate_f32(ba_tensor4 src, ba_tensor4 dst, int B, int S, int H, int D, void* stream) {
   using namespace ba;
-  BA_REQUIRE(D == 128, "ba_accumulate_f32: head dim %d unsupported (only 128)", D);
+  BA_REQUIRE(D == 128 || D == 64, "ba_accumulate_f32: head dim %d unsupported (64 or 128)", D);
+  const int lpr_log2 = D == 128 ? 5 : 4;
   BA_REQUIRE(B > 0 && S > 0 && H > 0 && src.ptr && dst.ptr, "ba_accumulate_f32: bad arguments");
   BA_REQUIRE(aligned16(src, 4) && aligned16(dst, 4), "ba_accumulate_f32: views must be 16-byte aligned");
-  const int64_t threads = (int64_t)B * S * H * 32;
+  const int64_t threads = ((int64_t)B * S * H) << lpr_log2;
   const unsigned blocks = (unsigned)((threads + 255) / 256);
   accumulate_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       (const float*)src.ptr, src.stride_b, src.stride_s, src.stride_h, (float*)dst.ptr, dst.stride_b, dst.stride_s,
-      dst.stride_h, B, S, H);
+      dst.stride_h, B, S, H, lpr_log2);
   BA_CHECK_CUDA(cudaGetLastError());
   return BA_OK;
 }

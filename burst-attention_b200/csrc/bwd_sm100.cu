@@ -47,16 +47,26 @@ __device__ __forceinline__ void reg_dec() {
 
 // ---- row statistics folded into the GEMMs ("fold") --------------------------------------------------------
 // P^T = exp2(S^T c - lse2[q]) and dS^T = P^T o (dP^T - delta[q]) need a per-COLUMN value in a thread = key-row
-// layout; reading them from shared memory costs 512 broadcast-LDS wavefronts per Q block on the shared-memory
-// data pipe this kernel is bound by (profiles/README.md).  Instead the tensor core adds them: one extra K = 16
-// step per GEMM,  S^T += 1[key] (x) (-lse/scale)[q],  dP^T += 1[key] (x) (-delta)[q],  with the fp32 value split
-// into three 16-bit parts (hi + lo + lolo: exact to fp32 round-off, products with 1.0 are exact, fp32 accumulate).
-// Operand tiles are K-major, NO swizzle (core matrix = 8 rows x 16 B, contiguous):
-//   B (per Q block, written by the loader warp): row q = [l0 l1 l2 d0 d1 d2 0 0]; 16 row groups x 128 B = 2 KiB;
-//     its second K chunk (k = 8..15) re-reads the first (LBO = 0): harmless, A is zero there;
-//   A (constant): ONE 128-byte core matrix of identical rows [1 1 1 0 0 0 0 0] (lse) or [0 0 0 1 1 1 0 0]
-//     (delta) shared by all 16 row groups (SBO = 0), second K chunk = a zero core matrix.
-// (make_smem_desc_noswz / split3: sm100_ptx.cuh)
+// layout; reading them from shared memory costs 512 broadcast-LDS wavefronts per Q block.  Instead the tensor core
+// adds them: one extra K = 16 step per GEMM,  S^T += 1[key] (x) (-lse/scale)[q],  dP^T += 1[key] (x) (-delta)[q],
+// with the fp32 value split into two 16-bit parts (hi + lo: 16 significant bits with bf16, 22 with fp16 -- an
+// error of <= 2^-17 |lse|/scale in the exponent, two orders of magnitude below the 16-bit rounding of P; the
+// products with 1.0 are exact and the accumulation is fp32).
+// Operand tiles are K-major, NO swizzle (core matrix = 8 rows x 16 B, contiguous; sm100_ptx.cuh):
+//   B (written by the loader warp, 2 KiB): row q = 8 slots = [l0 l1 d0 d1 | l0' l1' d0' d1']: the first four belong
+//     to even Q blocks, the last four to odd ones, so the statistics of block it+1 are written (8-byte stores) while
+//     MMAs of block it still read their half; the tile is zeroed at kernel start (a slot nobody has written must
+//     not hold a NaN pattern: it meets a 0 of the A operand).  Its second K chunk (k = 8..15) re-reads the first
+//     (LBO = 0): harmless, A is zero there;
+//   A (constant): ONE 128-byte core matrix of identical rows per pattern -- ones in the two slots to pick, zeros
+//     elsewhere -- shared by all 16 row groups (SBO = 0): lse/even, delta/even, lse/odd, delta/odd, and a zero core
+//     matrix that serves as every pattern's second K chunk.
+template <bool kBF16>
+BA_DEVICE void split2(float x, uint32_t& h0, uint32_t& h1) {
+  h0 = to16<kBF16>(x);
+  h1 = to16<kBF16>(x - from16<kBF16>(h0));
+}
+
 struct BwdParams {
   const float* lse;
   int64_t lse_sb, lse_sh;
@@ -71,6 +81,7 @@ struct BwdParams {
   int causal, causal_off;
   const float* bias;  // optional additive bias per key [B|1, H, Sk] (fp32), or null
   int64_t bias_sb, bias_sh;
+  int mma_order;  // 1: dV, dP, S', dK, dQ per Q block (default); 0: round 1's dV, S', dK, dQ, dP'
   int* sem;     // deterministic mode: [B][H][nQ] turn counters ordering the dQ reductions by key block; else null
   int* ticket;  // deterministic mode: [B][H] key-block tickets (a CTA's key block = the order in which it STARTED)
 };
@@ -107,8 +118,8 @@ struct BwdLayout {
   static constexpr int kOffDS = kOffDO + kTileB;
   static constexpr int kOffDQ = kOffDS + kDsTileB;    // 2 staging boxes
   static constexpr int kOffStat = kOffDQ + 2 * kDqStageB;  // fold: [128 q rows][16 B] row-stat operand tile; else [2][lse2|delta] fp32
-  static constexpr int kOffFoldA = kOffStat + 2 * 2 * kTile * 4;  // fold: [ones(lse) 128 B][ones(delta) 128 B][zeros 128 B]
-  static constexpr int kOffBar = kOffFoldA + 512;
+  static constexpr int kOffFoldA = kOffStat + 2 * 2 * kTile * 4;  // fold: 4 constant one-patterns + 1 zero core matrix, 128 B each
+  static constexpr int kOffBar = kOffFoldA + 640;
   static constexpr int kSmemBytes = kOffBar + 256;  // no align slack: the dynamic smem base is checked to be 1 KiB aligned
   static_assert(kSmemBytes <= 232448, "backward kernel exceeds 227 KiB of shared memory");
 };
@@ -180,13 +191,13 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&bars->dkv_full, 1);
       fence_mbar_init();
     }
-    if (kFold && lane < 24) {  // constant A operands of the row-stat K steps: 3 core matrices of 8 x 16 B
-      constexpr uint32_t one = kBF16 ? 0x3F80u : 0x3C00u;
-      const int m = lane >> 3;  // 0: ones in the lse slots 0..2, 1: ones in the delta slots 3..5, 2: zeros
-      uint4 row = make_uint4(0u, 0u, 0u, 0u);
-      if (m == 0) row = make_uint4(one | (one << 16), one, 0u, 0u);
-      if (m == 1) row = make_uint4(0u, one << 16, one | (one << 16), 0u);
-      *reinterpret_cast<uint4*>(smem + kOffFoldA + lane * 16) = row;
+    if constexpr (kFold) {  // constant A operands of the row-stat K steps: 5 core matrices of 8 rows x 16 B
+      constexpr uint32_t one2 = kBF16 ? 0x3F803F80u : 0x3C003C00u;
+      for (int i = lane; i < 40; i += 32) {
+        const int m = i >> 3;  // 0: lse/even (slots 0,1)  1: delta/even (2,3)  2: lse/odd (4,5)  3: delta/odd (6,7)  4: zeros
+        *reinterpret_cast<uint4*>(smem + kOffFoldA + i * 16) =
+            make_uint4(m == 0 ? one2 : 0u, m == 1 ? one2 : 0u, m == 2 ? one2 : 0u, m == 3 ? one2 : 0u);
+      }
       fence_proxy_async_smem();
     }
     __syncwarp();
@@ -205,6 +216,13 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 13) {
     // ============================================================ loader
     reg_dec<64>();
+    if constexpr (kFold) {  // (see the fold comment: unwritten slots must read as 0)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(smem + kOffStat + (lane + 32 * j) * 16) = make_uint4(0u, 0u, 0u, 0u);
+      fence_proxy_async_smem();
+      __syncwarp();
+    }
     if (lane == 0) {
       mbar_arrive_expect_tx(&bars->kv_full, 2 * kTileB);
       for (int half = 0; half < kBoxes; ++half) {
@@ -235,25 +253,23 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tma_load_4d(sQ + st * kTileB + half * kBoxB, &tmQ, &bars->q_full[st], half * 64, h, q0, b);
       }
       if constexpr (kFold) {
-        // ONE operand tile (lse and delta share a row): it may be overwritten once the MMAs that read it for the
-        // previous Q block -- S^T(it-1), then dP^T(it-1) -- have completed, i.e. dp_full(it-1).  dP^T(it) cannot be
-        // issued before this warp has loaded dO(it) below, so that barrier cannot run a phase ahead of us.
-        if (it > 0) mbar_wait(&bars->dp_full, (it - 1) & 1);
+        // this block's half of the operand rows (slots 4 (it & 1) ..): last read by the MMAs of block it - 2, which
+        // completed before q_empty[st] above was committed
         constexpr float kBig = kBF16 ? 1e30f : 60000.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int r = lane + 32 * j;
           const float xl = fmaxf(-sl[j] * p.inv_scale, -kBig);  // S^T + xl = (S^T c - lse2) / c
           const float xd = fminf(fmaxf(-sd[j], -kBig), kBig);
-          uint32_t l0, l1, l2, d0, d1, d2;
-          split3<kBF16>(xl, l0, l1, l2);
-          split3<kBF16>(xd, d0, d1, d2);
-          *reinterpret_cast<uint4*>(smem + kOffStat + (r >> 3) * 128 + (r & 7) * 16) =
-              make_uint4(l0 | (l1 << 16), l2 | (d0 << 16), d1 | (d2 << 16), 0u);
+          uint32_t l0, l1, d0, d1;
+          split2<kBF16>(xl, l0, l1);
+          split2<kBF16>(xd, d0, d1);
+          *reinterpret_cast<uint2*>(smem + kOffStat + (r >> 3) * 128 + (r & 7) * 16 + st * 8) =
+              make_uint2(l0 | (l1 << 16), d0 | (d1 << 16));
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->stat_full[0]);
+        if (lane == 0) mbar_arrive(&bars->stat_full[st]);
       } else {
         // lse in log2 units, delta: read by the compute warps (broadcast LDS)
         float* stat = sStat + st * 2 * kTile;
@@ -293,8 +309,8 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
       // row-stat K steps (kFold): no-swizzle K-major tiles, see the comment at make_smem_desc_noswz
       const uint32_t sFA = smem_u32(smem + kOffFoldA);
-      const uint64_t dA_lse = make_smem_desc_noswz(sFA, 256, 0);        // ones in slots 0..2 | zero chunk
-      const uint64_t dA_dl = make_smem_desc_noswz(sFA + 128, 128, 0);   // ones in slots 3..5 | zero chunk
+      // pattern i at sFA + 128 i (lse/even, delta/even, lse/odd, delta/odd), second K chunk = the zero matrix at + 512
+      auto dA_pat = [&](int i) -> uint64_t { return make_smem_desc_noswz(sFA + 128 * i, (4 - i) * 128, 0); };
       const uint64_t dB_stat = make_smem_desc_noswz(smem_u32(smem + kOffStat), 0, 128);
 
       auto kstep_k = [](int kk) -> uint32_t { return (kk >> 2) * kBoxB + (kk & 3) * 32; };  // K-major k-step
@@ -306,16 +322,16 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int kk = 0; kk < kKSteps; ++kk)
           umma_ss(tS, desc_advance(dK_k, kstep_k(kk)), desc_advance(dQ_k, kstep_k(kk)), id_kk, kk > 0);
         if constexpr (kFold) {
-          mbar_wait(&bars->stat_full[0], it_of_block & 1);
+          mbar_wait(&bars->stat_full[it_of_block & 1], (it_of_block >> 1) & 1);
           tc_fence_after();
-          umma_ss(tS, dA_lse, dB_stat, id_kk, 1);
+          umma_ss(tS, dA_pat(2 * (it_of_block & 1)), dB_stat, id_kk, 1);
         }
       };
-      auto issue_dP = [&]() {  // dP^T = V dO^T  (kFold: ... - delta; same operand tile as the S^T just issued)
+      auto issue_dP = [&](int it_of_block) {  // dP^T = V dO^T  (kFold: ... - delta; S^T of the block was issued before)
 #pragma unroll
         for (int kk = 0; kk < kKSteps; ++kk)
           umma_ss(tDP, desc_advance(dV_k, kstep_k(kk)), desc_advance(dDO_k, kstep_k(kk)), id_kk, kk > 0);
-        if constexpr (kFold) umma_ss(tDP, dA_dl, dB_stat, id_kk, 1);
+        if constexpr (kFold) umma_ss(tDP, dA_pat(2 * (it_of_block & 1) + 1), dB_stat, id_kk, 1);
       };
       auto issue_dV = [&](bool acc) {  // dV += P^T dO ; P^T cols: q 0..63 at [0,32), q 64..127 at [64,96)
 #pragma unroll
@@ -344,17 +360,34 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_after();
       issue_S(0, 0);
       umma_commit(&bars->s_full);
-      mbar_wait(&bars->do_full, 0);
-      tc_fence_after();
-      issue_dP();
-      umma_commit(&bars->dp_full);
+      // Issue order per Q block.  Default (mma_order 1): dV, dP^T, S^T(next), dK, dQ -- dV (which only needs P^T)
+      // runs while the drain warps empty the previous block's dQ, so dP^T's wait for those TMEM columns (MMA
+      // complete -> commit -> drain wakes -> tcgen05.ld -> arrive -> issue, ~700 clk with nothing else for the
+      // in-order tensor pipe to run) is covered; the compute warps idle between P^T and dS^T instead, which costs
+      // nothing: they are not the bound.  mma_order 0 is round 1's dV, S^T(next), dK, dQ, dP^T(next).
+      const bool late_dp = p.mma_order == 0;
+      if (late_dp) {
+        mbar_wait(&bars->do_full, 0);
+        tc_fence_after();
+        issue_dP(0);
+        umma_commit(&bars->dp_full);
+      }
       for (int it = 0; it < n_it; ++it) {
         const int st = it & 1;
         const bool have_next = it + 1 < n_it;
         mbar_wait(&bars->p_ready, it & 1);
         tc_fence_after();
         issue_dV(it > 0);
-        umma_commit(&bars->do_empty);
+        if (!late_dp) {
+          mbar_wait(&bars->do_full, it & 1);
+          if (it > 0) mbar_wait(&bars->dq_free, (it - 1) & 1);
+          tc_fence_after();
+        }
+        if (!late_dp) {
+          issue_dP(it);
+          umma_commit(&bars->dp_full);
+        }
+        umma_commit(&bars->do_empty);  // dV (and, by now, dP^T) of this block have read the dO tile
         if (have_next) {
           mbar_wait(&bars->q_full[st ^ 1], ((it + 1) >> 1) & 1);
           tc_fence_after();
@@ -367,11 +400,11 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         umma_commit(&bars->q_empty[st]);
         issue_dQ();
         umma_commit(&bars->dq_full);
-        if (have_next) {
+        if (late_dp && have_next) {
           mbar_wait(&bars->do_full, (it + 1) & 1);
           mbar_wait(&bars->dq_free, it & 1);
           tc_fence_after();
-          issue_dP();
+          issue_dP(it + 1);
           umma_commit(&bars->dp_full);
         }
       }
@@ -681,6 +714,11 @@ extern "C" int ba_bwd_chunk_bias(ba_tensor4 d_o, ba_tensor4 q, ba_tensor4 k, ba_
   p.causal = mask_mode == BA_MASK_CAUSAL;
   p.causal_off = causal_offset;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const int order = [] {
+    const char* e = getenv("BA_BWD_ORDER");  // A/B knob, read once
+    return e ? atoi(e) : 1;
+  }();
+  p.mma_order = order;
   p.sem = p.ticket = nullptr;
   if (flags & BA_BWD_DETERMINISTIC) {
     const size_t n_turn = (size_t)B * H * ((Sq + kTile - 1) / kTile);

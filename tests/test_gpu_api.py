@@ -119,7 +119,17 @@ def test_key_vector_bias(monkeypatch, D, causal):
                                                                    bias=bias.cpu())
         if causal:  # row 0 sees only key 0 (finite bias); rows whose visible keys are all masked do not exist here
             assert not torch.isnan(o_ref).any()
-        for got, ref in ((o, o_ref), (dq, dq_ref), (dk, dk_ref), (dv, dv_ref)):
+        # a bias of a few units makes the softmax peaky (gradients of O(1..10)): the stated bf16 tolerance with a wider
+        # absolute floor, plus the size-independent yardstick "not worse than 2x a plain bf16 PyTorch implementation"
+        qp, kp, vp = (t.detach().permute(0, 2, 1, 3).clone().requires_grad_() for t in (q, k, v))
+        sc = (qp @ kp.transpose(-1, -2)) * D ** -0.5 + bias
+        if causal:
+            sc = sc.masked_fill(~torch.ones(s, s, dtype=torch.bool, device="cuda").tril(), float("-inf"))
+        op = torch.softmax(sc.float(), -1).to(dtype) @ vp
+        plain = [t.permute(0, 2, 1, 3) for t in (op, *torch.autograd.grad(op, (qp, kp, vp), do.permute(0, 2, 1, 3)))]
+        for got, ref, pl in zip((o, dq, dk, dv), (o_ref, dq_ref, dk_ref, dv_ref), plain):
             assert not torch.isnan(got).any()
-            torch.testing.assert_close(got.double().cpu(), ref, **TOL[dtype])
+            torch.testing.assert_close(got.double().cpu(), ref, rtol=1.6e-2, atol=6e-2)
+            e_ours, e_plain = (got.double().cpu() - ref).abs().max().item(), (pl.double().cpu() - ref).abs().max().item()
+            assert e_ours <= 2 * e_plain + 1e-3, (e_ours, e_plain)
         assert torch.all(dk[:, 5::7] == 0) and torch.all(dv[:, 5::7] == 0)  # masked keys get no gradient
