@@ -81,7 +81,6 @@ struct BwdParams {
   int causal, causal_off;
   const float* bias;  // optional additive bias per key [B|1, H, Sk] (fp32), or null
   int64_t bias_sb, bias_sh;
-  int mma_order;  // 1: dV, dP, S', dK, dQ per Q block (default); 0: round 1's dV, S', dK, dQ, dP'
   int* sem;     // deterministic mode: [B][H][nQ] turn counters ordering the dQ reductions by key block; else null
   int* ticket;  // deterministic mode: [B][H] key-block tickets (a CTA's key block = the order in which it STARTED)
 };
@@ -360,34 +359,20 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc_fence_after();
       issue_S(0, 0);
       umma_commit(&bars->s_full);
-      // Issue order per Q block.  Default (mma_order 1): dV, dP^T, S^T(next), dK, dQ -- dV (which only needs P^T)
-      // runs while the drain warps empty the previous block's dQ, so dP^T's wait for those TMEM columns (MMA
-      // complete -> commit -> drain wakes -> tcgen05.ld -> arrive -> issue, ~700 clk with nothing else for the
-      // in-order tensor pipe to run) is covered; the compute warps idle between P^T and dS^T instead, which costs
-      // nothing: they are not the bound.  mma_order 0 is round 1's dV, S^T(next), dK, dQ, dP^T(next).
-      const bool late_dp = p.mma_order == 0;
-      if (late_dp) {
-        mbar_wait(&bars->do_full, 0);
-        tc_fence_after();
-        issue_dP(0);
-        umma_commit(&bars->dp_full);
-      }
+      // Issue order per Q block: dV, S^T(next), dK, dQ, dP^T(next).  dP^T(next) reuses the TMEM columns of dQ and
+      // waits for the drain warps.  (Measured alternative, same box: dV, dP^T, S^T(next), dK, dQ -- which runs dV under
+      // that wait but delivers dP^T later to the compute warps -- is 5 % slower: 1027 vs 1082 TFLOP/s.)
+      mbar_wait(&bars->do_full, 0);
+      tc_fence_after();
+      issue_dP(0);
+      umma_commit(&bars->dp_full);
       for (int it = 0; it < n_it; ++it) {
         const int st = it & 1;
         const bool have_next = it + 1 < n_it;
         mbar_wait(&bars->p_ready, it & 1);
         tc_fence_after();
         issue_dV(it > 0);
-        if (!late_dp) {
-          mbar_wait(&bars->do_full, it & 1);
-          if (it > 0) mbar_wait(&bars->dq_free, (it - 1) & 1);
-          tc_fence_after();
-        }
-        if (!late_dp) {
-          issue_dP(it);
-          umma_commit(&bars->dp_full);
-        }
-        umma_commit(&bars->do_empty);  // dV (and, by now, dP^T) of this block have read the dO tile
+        umma_commit(&bars->do_empty);
         if (have_next) {
           mbar_wait(&bars->q_full[st ^ 1], ((it + 1) >> 1) & 1);
           tc_fence_after();
@@ -400,7 +385,7 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         umma_commit(&bars->q_empty[st]);
         issue_dQ();
         umma_commit(&bars->dq_full);
-        if (late_dp && have_next) {
+        if (have_next) {
           mbar_wait(&bars->do_full, (it + 1) & 1);
           mbar_wait(&bars->dq_free, it & 1);
           tc_fence_after();
@@ -714,11 +699,6 @@ extern "C" int ba_bwd_chunk_bias(ba_tensor4 d_o, ba_tensor4 q, ba_tensor4 k, ba_
   p.causal = mask_mode == BA_MASK_CAUSAL;
   p.causal_off = causal_offset;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static const int order = [] {
-    const char* e = getenv("BA_BWD_ORDER");  // A/B knob, read once
-    return e ? atoi(e) : 1;
-  }();
-  p.mma_order = order;
   p.sem = p.ticket = nullptr;
   if (flags & BA_BWD_DETERMINISTIC) {
     const size_t n_turn = (size_t)B * H * ((Sq + kTile - 1) / kTile);
