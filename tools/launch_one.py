@@ -24,6 +24,7 @@ ap.add_argument("--off", type=int, default=0)
 ap.add_argument("--n", type=int, default=3)
 ap.add_argument("--time", action="store_true")
 ap.add_argument("--deterministic", action="store_true")
+ap.add_argument("--fresh", action="store_true", help="fwd: first+last in one launch (no carried state, 16-bit output)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(0)
@@ -41,7 +42,7 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 if a.kernel == "fwd":
     e0.record()
     for i in range(a.n):
-        ops.fwd_chunk(q, k, v, o_acc, lse, out, scale, a.causal, a.off, False, False, 1)  # carried-state form
+        ops.fwd_chunk(q, k, v, o_acc, lse, out, scale, a.causal, a.off, a.fresh, a.fresh, 1)  # default: carried-state form
     e1.record()
 else:
     delta = torch.empty(1, a.H, a.Sq, device=dev, dtype=torch.float32)
