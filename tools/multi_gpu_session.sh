@@ -20,12 +20,12 @@ grep -E "ring_check|MISMATCH|Error|rc=" gpurun_out/ring_check_${TAG}_n${N}_ce.tx
 CE_OK=0; grep -q "rc=0" gpurun_out/ring_check_${TAG}_n${N}_ce.txt && ! grep -q FAIL gpurun_out/ring_check_${TAG}_n${N}_ce.txt && CE_OK=1
 echo "CE_OK=$CE_OK"
 
-# 3. the reference itself on this box (8 GPUs only: the north-star denominator)
+# 3. the reference itself on this box (the north-star denominator is its 8-GPU number; smaller N for the record)
+run timeout 400 $TR --master-port $(port) tools/ref_on_b200.py --seq 262144 --steps 3 --warmup 2 --out gpurun_out/ref_on_b200_${TAG}.json > gpurun_out/ref_on_b200_${TAG}_n${N}_c3.log 2>&1
 if [ "$N" -ge 8 ]; then
-  run timeout 300 $TR --master-port $(port) tools/ref_on_b200.py --seq 262144 --steps 3 --warmup 2 --out gpurun_out/ref_on_b200_${TAG}.json > gpurun_out/ref_on_b200_${TAG}_c3.log 2>&1
-  run timeout 300 $TR --master-port $(port) tools/ref_on_b200.py --seq 524288 --causal --steps 2 --warmup 1 --out gpurun_out/ref_on_b200_${TAG}.json > gpurun_out/ref_on_b200_${TAG}_c4.log 2>&1
-  cat gpurun_out/ref_on_b200_${TAG}.json; tail -3 gpurun_out/ref_on_b200_${TAG}_c3.log
+  run timeout 300 $TR --master-port $(port) tools/ref_on_b200.py --seq 524288 --causal --steps 2 --warmup 1 --out gpurun_out/ref_on_b200_${TAG}.json > gpurun_out/ref_on_b200_${TAG}_n${N}_c4.log 2>&1
 fi
+cat gpurun_out/ref_on_b200_${TAG}.json; tail -3 gpurun_out/ref_on_b200_${TAG}_n${N}_c3.log
 
 # 4. bench: flat ring over NCCL (headline config first, with e2e and the comm A/B), then the other configurations
 CFG="65536,524288c"; [ "$N" -ge 8 ] && [ "${FULL:-0}" = 1 ] && CFG="65536,524288c,1048576"
