@@ -17,8 +17,6 @@ constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays <= 2^8
 
 struct FwdParams {
-  const uint16_t* q;  // raw 16-bit Q view (fwd1: rows are staged by the softmax threads into TMEM)
-  int64_t q_sb, q_ss, q_sh;
   float* o_acc;
   int64_t oacc_sb, oacc_ss, oacc_sh;
   float* lse;
@@ -36,8 +34,5 @@ struct FwdParams {
   int store_lowp;
 };
 
-
-// one Q tile per CTA, 2-CTA cluster with multicast K/V, both GEMMs TS-form (fwd1_sm100.cu); head dim 128, no bias
-int launch_fwd1(int dtype, const CUtensorMap& tmK64, const CUtensorMap& tmV64, const FwdParams& p, cudaStream_t stream);
 
 }  // namespace ba

@@ -524,8 +524,6 @@ extern "C" int ba_fwd_chunk_bias(ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_ro
   if ((rc = make_tensor_map(&tmV, v, B, Sk, H, D, dt, 2, 64, kBlockN, true))) return rc;
 
   FwdParams p;
-  p.q = static_cast<const uint16_t*>(q.ptr);
-  p.q_sb = q.stride_b, p.q_ss = q.stride_s, p.q_sh = q.stride_h;
   p.o_acc = static_cast<float*>(o_acc.ptr);
   p.oacc_sb = o_acc.stride_b, p.oacc_ss = o_acc.stride_s, p.oacc_sh = o_acc.stride_h;
   p.lse = lse.ptr;
@@ -541,19 +539,6 @@ extern "C" int ba_fwd_chunk_bias(ba_tensor4 q, ba_tensor4 k, ba_tensor4 v, ba_ro
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p.bias = key_bias.ptr, p.bias_sb = key_bias.stride_b, p.bias_sh = key_bias.stride_h;
   p.inv_scale = 1.f / scale;
-  // BA_FWD_IMPL (read once): 1 = one Q tile per CTA, cluster multicast, TS-form QK^T (fwd1_sm100.cu; head dim 128,
-  // no bias); 2 = two Q tiles per CTA (this file)
-  static const int impl = [] {
-    const char* e = getenv("BA_FWD_IMPL");
-    return e ? atoi(e) : 2;
-  }();
-  if (impl == 1 && D == 128 && !key_bias.ptr && (reinterpret_cast<uintptr_t>(q.ptr) & 15) == 0 && q.stride_b % 8 == 0 &&
-      q.stride_s % 8 == 0 && q.stride_h % 8 == 0) {
-    CUtensorMap tmK64, tmV64;
-    if ((rc = make_tensor_map(&tmK64, k, B, Sk, H, D, dt, 2, 64, 64, true))) return rc;
-    if ((rc = make_tensor_map(&tmV64, v, B, Sk, H, D, dt, 2, 64, 64, true))) return rc;
-    return launch_fwd1(dtype, tmK64, tmV64, p, st);
-  }
   if (key_bias.ptr)
     return D == 64 ? launch_fwd_dt<64, true>(dtype, tmQ, tmK, tmV, p, st) : launch_fwd_dt<128, true>(dtype, tmQ, tmK, tmV, p, st);
   return D == 64 ? launch_fwd_dt<64, false>(dtype, tmQ, tmK, tmV, p, st) : launch_fwd_dt<128, false>(dtype, tmQ, tmK, tmV, p, st);
