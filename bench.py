@@ -260,6 +260,11 @@ def _dense_fp32(q, k, v, do, causal):
     return [t.permute(0, 2, 1, 3) for t in (o, *g)]
 
 
+def _ring_transport():
+    from burst_attn import comm
+    return comm.default_transport()
+
+
 def ring_parity(world, rank, dev, double_group):
     from burst_attn import burst_attn_func, burst_attn_func_striped
     cases, failed, worst = 0, [], 0.0
@@ -581,7 +586,7 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"burst_attn_func fwd+bwd, bs={Bn} S={S} (S_local={S_loc}) H=32 d=128 bf16 "
                                    f"{'causal zigzag' if args.causal else 'non-causal contiguous'} shards, "
-                                   f"{'local kernel, no ring' if world == 1 else f'{world}-rank ring over ' + ('copy engines + CUDA IPC' if os.environ.get('BA_RING_TRANSPORT') == 'ce' else 'NCCL')}"
+                                   f"{'local kernel, no ring' if world == 1 else f'{world}-rank ring over ' + ('copy engines + CUDA IPC' if _ring_transport() == 'ce' else 'NCCL')}"
                                    f"{f' (double ring, intra {args.double_ring})' if args.double_ring and world > 1 else ''}",
                        "global_batch": Bn, "seq_len": S, "parallelism": f"sp{world}",
                        "l2": "inputs (>= 256 MiB per tensor per rank) exceed the 126 MB L2; no flush needed"},

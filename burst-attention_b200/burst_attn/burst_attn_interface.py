@@ -59,9 +59,10 @@ def get_partition_id(double_group, r):
     return ((a - (r - 1) // L) % M) * L + (b - (r - 1) % L) % L
 
 
-# Hierarchical ring over NCCL: opt-in until `RING_CHECK_DOUBLE=<L> torchrun tests/ring_check.py` has passed on
-# GPUs (the flat ring over process_group is always correct); flipped to "1" once profiles/ holds that log.
-_DOUBLE_RING_DEFAULT = "0"
+# Hierarchical ring over NCCL: on when the caller passes double_group (BA_DOUBLE_RING=0 forces the flat ring over
+# process_group).  `RING_CHECK_DOUBLE=2,4 torchrun tests/ring_check.py` passed on 8 x B200 for intra-node rings of 2
+# and of 4 (profiles/ring_check_r02_n8_nccl.txt).
+_DOUBLE_RING_DEFAULT = "1"
 
 
 class _Topology:

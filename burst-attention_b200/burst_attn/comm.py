@@ -10,9 +10,10 @@ awaited by ``wait``.  Two transports:
   sync (the reference's BMTrain side-stream variant, comm.py:267-283,313-317,
   is the model).  One communicator per (process group, tag), cached -- the
   reference builds a fresh ``Ring`` per call (burst_attn_interface.py:205,265,268).
-  With ``BA_RING_TRANSPORT=ce`` the flat ring instead pushes its hops with the copy
-  engines into a ring-owned, IPC-mapped receive arena (csrc/ring_ce.cu): zero SMs,
-  for shards short enough that NCCL's SM-resident kernels would be exposed.  Receive
+  When all ranks share a node (``default_transport``; or ``BA_RING_TRANSPORT=ce``) the flat ring instead
+  pushes its hops with the copy engines into a ring-owned, IPC-mapped receive arena
+  (csrc/ring_ce.cu): zero SMs, so the hop neither slows the tile kernels down nor -- for short
+  shards -- stays exposed behind them as NCCL's SM-resident kernels do.  Receive
   buffers then come from ``Ring.empty_like`` (a bump allocator over the arena that
   every rank drives identically, so offsets are symmetric).
 * ``torch`` (CPU tensors under gloo, used by the world_size-2 CPU tests of the
@@ -189,13 +190,30 @@ def destroy_rings() -> None:
 
 
 # --------------------------------------------------------------------------- #
+def default_transport() -> str:
+    """Transport of a flat ring when the caller does not name one: ``BA_RING_TRANSPORT`` if set; otherwise the copy
+    engines (``ce``) when every rank of the job runs on this node -- torchrun's LOCAL_WORLD_SIZE equals the world
+    size -- and NCCL in every other case (several nodes, or a launcher that does not say).  Measured on 8 x B200
+    (profiles/README_r02.md): ce 8181 vs nccl 8091 TFLOPS/s at S = 262144 (NCCL's SM-resident send/recv kernels slow
+    the tile kernels down while they co-run) and 7770 vs 6178 at S = 65536 (there NCCL's hop is exposed)."""
+    env = os.environ.get("BA_RING_TRANSPORT")
+    if env:
+        return env
+    try:
+        local = int(os.environ.get("LOCAL_WORLD_SIZE", "0"))
+    except ValueError:
+        local = 0
+    world = get_world_size(None)
+    return "ce" if (world > 1 and local == world) else "nccl"
+
+
 class Ring:
     """Single flat ring over ``process_group``: send to (rank+1)%W, receive from (rank-1)%W."""
 
     def __init__(self, process_group=None, local_group=(None, None), dq: bool = False, tag: Optional[str] = None,
                  transport: Optional[str] = None):
         self.comm = process_group
-        self.transport = transport or os.environ.get("BA_RING_TRANSPORT", "nccl")
+        self.transport = transport or default_transport()
         # "local": measurement only (bench.py --ab-comm): every hop becomes a device-local copy src -> dst on the
         # compute stream, i.e. the ring is replaced by a local buffer swap -- same kernels, same bytes through HBM,
         # nothing over NVLink -- the A/B partner that isolates exposed communication time (results are wrong)

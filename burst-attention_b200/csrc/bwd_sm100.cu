@@ -258,7 +258,7 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int r = lane + 32 * j;
-          const float xl = fmaxf(-sl[j] * p.inv_scale, -kBig);  // S^T + xl = (S^T c - lse2) / c
+          const float xl = fminf(fmaxf(-sl[j] * p.inv_scale, -kBig), kBig);  // S^T + xl = (S^T c - lse2) / c
           const float xd = fminf(fmaxf(-sd[j], -kBig), kBig);
           uint32_t l0, l1, d0, d1;
           split2<kBF16>(xl, l0, l1);
