@@ -52,3 +52,21 @@ def test_reference_arm_prints_one_json_line():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference"],
                          capture_output=True, text=True, timeout=120, env=dict(os.environ, RANK="1"))
     assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+def test_default_ring_transport(monkeypatch):
+    """copy engines when every rank of the job is on this node (torchrun's LOCAL_WORLD_SIZE == world size), NCCL
+    otherwise; BA_RING_TRANSPORT always wins."""
+    sys.path.insert(0, os.path.join(ROOT, "burst-attention_b200"))
+    from burst_attn import comm
+    monkeypatch.delenv("BA_RING_TRANSPORT", raising=False)
+    for world, local, want in ((8, "8", "ce"), (8, "4", "nccl"), (8, None, "nccl"), (1, "1", "nccl"), (2, "x", "nccl")):
+        monkeypatch.setattr(comm, "get_world_size", lambda g=None, w=world: w)
+        if local is None:
+            monkeypatch.delenv("LOCAL_WORLD_SIZE", raising=False)
+        else:
+            monkeypatch.setenv("LOCAL_WORLD_SIZE", local)
+        assert comm.default_transport() == want, (world, local)
+    monkeypatch.setenv("BA_RING_TRANSPORT", "nccl")
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert comm.default_transport() == "nccl"
