@@ -32,19 +32,6 @@ BA_DEVICE float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^x on the FMA/ALU pipes (no MUFU): Cody-Waite split with the 1.5*2^23 magic constant,
-// cubic minimax for 2^f on [-0.5, 0.5] (max rel. error 1.5e-4, below 16-bit P precision), exponent
-// spliced in with an integer add.  Valid for x <= ~100; x < -126 (incl. -inf) returns ~1e-38.
-BA_DEVICE float ex2_poly(float x) {
-  x = fmaxf(x, -126.f);
-  const float t = x + 12582912.f;
-  const float n = t - 12582912.f;
-  const float f = x - n;
-  float p = fmaf(0.05517167f, f, 0.24261113f);
-  p = fmaf(p, f, 0.69326097f);
-  p = fmaf(p, f, 0.99992806f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
 BA_DEVICE float lg2(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
