@@ -343,9 +343,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the ring parity protocol that runs before timing")
-    ap.add_argument("--ab-comm", action="store_true",
-                    help="also time the step with the ring replaced by a local buffer swap (BA_RING_TRANSPORT=local): "
-                         "the A/B partner that isolates exposed ring-communication time")
+    ap.add_argument("--ab-comm", action="store_true", help="(default for N > 1; kept for older command lines)")
+    ap.add_argument("--no-ab-comm", action="store_true",
+                    help="skip the A/B partner of multi-GPU runs: the step with the ring replaced by a local buffer swap "
+                         "(BA_RING_TRANSPORT=local), which isolates exposed ring-communication time (comm_ab in the JSON line)")
     ap.add_argument("--configs", default="", help="comma list of extra runs in the same process group, e.g. "
                     "'262144,524288c,1048576' (c = causal zigzag); one JSON line each (multi-GPU sessions are "
                     "expensive to start)")
@@ -557,7 +558,7 @@ def _bench_one(args, world, rank, local, dev, W, K, ops, burst_attn_func):
 
     # ---- A/B: the same step with the ring replaced by a local buffer swap -> exposed ring-communication time
     ab = None
-    if args.ab_comm and world > 1:
+    if not args.no_ab_comm and world > 1:
         prev_tr = os.environ.get("BA_RING_TRANSPORT")
         os.environ["BA_RING_TRANSPORT"] = "local"
         try:
