@@ -10,9 +10,10 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 port() { echo $((29500 + RANDOM % 400)); }
 run() { echo "=== $*"; "$@"; echo "--- rc=$?"; }
 
+# (the copy-engine ring is the default on one node; the NCCL steps name their transport)
 # 1. ring parity, reference protocol: flat ring over NCCL (+ hierarchical rings when N >= 4)
 DBL=""; [ "$N" -ge 4 ] && DBL="2"; [ "$N" -ge 8 ] && DBL="2,4"
-RING_CHECK_DOUBLE=$DBL run timeout 300 $TR --master-port $(port) tests/ring_check.py > gpurun_out/ring_check_${TAG}_n${N}_nccl.txt 2>&1
+BA_RING_TRANSPORT=nccl RING_CHECK_DOUBLE=$DBL run timeout 300 $TR --master-port $(port) tests/ring_check.py > gpurun_out/ring_check_${TAG}_n${N}_nccl.txt 2>&1
 grep -E "ring_check|MISMATCH|Error|rc=" gpurun_out/ring_check_${TAG}_n${N}_nccl.txt | tail -20
 # 2. the same over the copy-engine transport (first runs of csrc/ring_ce.cu): short timeout
 BA_RING_TRANSPORT=ce run timeout 180 $TR --master-port $(port) tests/ring_check.py > gpurun_out/ring_check_${TAG}_n${N}_ce.txt 2>&1
@@ -29,12 +30,12 @@ cat gpurun_out/ref_on_b200_${TAG}.json; tail -3 gpurun_out/ref_on_b200_${TAG}_n$
 
 # 4. bench: flat ring over NCCL (headline config first, with e2e and the comm A/B), then the other configurations
 CFG="65536,524288c"; [ "$N" -ge 8 ] && [ "${FULL:-0}" = 1 ] && CFG="65536,524288c,1048576"
-run timeout 400 $TR --master-port $(port) bench.py --gpus $N --steps 3 --warmup 3 --ab-comm > gpurun_out/bench_${TAG}_n${N}_nccl.json 2> gpurun_out/bench_${TAG}_n${N}_nccl.err
-run timeout 500 $TR --master-port $(port) bench.py --gpus $N --steps 2 --warmup 3 --ab-comm --no-e2e --no-parity --configs $CFG > gpurun_out/bench_${TAG}_n${N}_nccl_cfg.json 2> gpurun_out/bench_${TAG}_n${N}_nccl_cfg.err
+BA_RING_TRANSPORT=nccl run timeout 400 $TR --master-port $(port) bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_${TAG}_n${N}_nccl.json 2> gpurun_out/bench_${TAG}_n${N}_nccl.err
+BA_RING_TRANSPORT=nccl run timeout 500 $TR --master-port $(port) bench.py --gpus $N --steps 2 --warmup 3 --no-e2e --no-parity --configs $CFG > gpurun_out/bench_${TAG}_n${N}_nccl_cfg.json 2> gpurun_out/bench_${TAG}_n${N}_nccl_cfg.err
 # 4b. NCCL's send/recv kernels are SM-resident and slow the tile kernels down while they co-run (round 1: fwd +8.7 %
 #     at N = 8); the ring needs < 100 GB/s per hop, so cap the CTAs NCCL may use
 for c in ${NCCL_CTAS:-2 4}; do
-  BA_NCCL_MAX_CTAS=$c run timeout 300 $TR --master-port $(port) bench.py --gpus $N --steps 3 --warmup 3 --no-e2e --no-parity > gpurun_out/bench_${TAG}_n${N}_ncclcta${c}.json 2> gpurun_out/bench_${TAG}_n${N}_ncclcta${c}.err
+  BA_RING_TRANSPORT=nccl BA_NCCL_MAX_CTAS=$c run timeout 300 $TR --master-port $(port) bench.py --gpus $N --steps 3 --warmup 3 --no-e2e --no-parity > gpurun_out/bench_${TAG}_n${N}_ncclcta${c}.json 2> gpurun_out/bench_${TAG}_n${N}_ncclcta${c}.err
 done
 # 5. the same over the copy engines
 if [ "$CE_OK" = 1 ]; then
