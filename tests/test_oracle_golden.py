@@ -84,3 +84,27 @@ def test_whole_op_forward_matches_reference(golden):
     q, k, v = (T(golden[n]).permute(0, 2, 1, 3) for n in ("op_q", "op_k", "op_v"))
     o, _ = orc.dense_attention(q, k, v)
     torch.testing.assert_close(o, T(golden["op_o"]).permute(0, 2, 1, 3).double(), rtol=1e-4, atol=2e-5)
+
+
+def test_oracle_matches_the_installed_reference_cpu_ring():
+    """Second pin (besides the committed golden vectors): the UNMODIFIED reference installed in baseline/_ref, driven
+    through its own inter_normal_attn / inter_normal_attn_backward over a simulated 4-rank ring
+    (baseline/ref_shim.cpu_ring_step), against the oracle's dense attention.  Skipped where baseline/_ref is absent."""
+    import os
+    import sys
+    import pytest
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "baseline"))
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip("baseline/_ref not installed (python -c 'import __graft_entry__ as g; g.build()' in the build container)")
+    torch.manual_seed(0)
+    B, H, S, D = 1, 4, 512, 64
+    q, k, v, do = (torch.randn(B, H, S, D) for _ in range(4))
+    p = lambda t: t.permute(0, 2, 1, 3)  # noqa: E731  reference "normal" layout [B,H,S,D] -> oracle [B,S,H,D]
+    o_ref, _, dq_ref, dk_ref, dv_ref = orc.dense_attention_bwd(p(q), p(k), p(v), p(do))
+    for W in (1, 4):
+        o, dq, dk, dv, _, _ = ref_shim.cpu_ring_step(q, k, v, do, W, D ** -0.5)
+        for got, ref in ((o, o_ref), (dq, dq_ref), (dk, dk_ref), (dv, dv_ref)):
+            # floor: the reference's own +1e-5 inside log (burst_utils.py:71,73) and fp32 arithmetic
+            torch.testing.assert_close(p(got).double(), ref, rtol=1e-4, atol=2e-5)
