@@ -72,6 +72,14 @@ def _align(n: int, a: int = 1024) -> int:
     return (n + a - 1) // a * a
 
 
+class CopyEngineUnavailable(RuntimeError):
+    """The copy-engine transport could not be set up on at least one rank (e.g. a process that cannot see its
+    neighbours' GPUs, or no CUDA IPC in this container).  Raised on EVERY rank of the ring together."""
+
+
+_ce_disabled = False  # set once the copy-engine transport failed in this process: later rings go over NCCL
+
+
 class _NativeRing:
     def __init__(self, group, tag: str, device: torch.device, transport: str = "nccl"):
         self.lib = _n.lib()
@@ -130,15 +138,32 @@ class _NativeRing:
         base = ctypes.c_void_p()
         hbuf = (ctypes.c_uint8 * _n.IPC_HANDLE_BYTES)()
         with torch.cuda.device(self.device):
-            _n.check(self.lib.ba_ring_arena_create(self.handle, nbytes, ctypes.byref(base), hbuf),
-                     "ba_ring_arena_create")
-            handles: List[Optional[bytes]] = [None] * self.world
-            dist.all_gather_object(handles, bytes(hbuf), group=self.group)
-            prv = (ctypes.c_uint8 * _n.IPC_HANDLE_BYTES).from_buffer_copy(handles[(self.rank - 1) % self.world])
-            nxt = (ctypes.c_uint8 * _n.IPC_HANDLE_BYTES).from_buffer_copy(handles[(self.rank + 1) % self.world])
-            _n.check(self.lib.ba_ring_arena_connect(self.handle, prv, nxt), "ba_ring_arena_connect")
+            # Every rank goes through the same collectives whether or not its own step worked, and all ranks then
+            # agree: either everyone has a connected arena or everyone raises CopyEngineUnavailable (-> NCCL).
+            err = self._try(lambda: self.lib.ba_ring_arena_create(self.handle, nbytes, ctypes.byref(base), hbuf),
+                            "ba_ring_arena_create")
+            gathered: List[Optional[tuple]] = [None] * self.world
+            dist.all_gather_object(gathered, (err is None, bytes(hbuf)), group=self.group)
+            if not all(g[0] for g in gathered):
+                raise CopyEngineUnavailable(err or "a peer rank could not create its receive arena")
+            prv = (ctypes.c_uint8 * _n.IPC_HANDLE_BYTES).from_buffer_copy(gathered[(self.rank - 1) % self.world][1])
+            nxt = (ctypes.c_uint8 * _n.IPC_HANDLE_BYTES).from_buffer_copy(gathered[(self.rank + 1) % self.world][1])
+            err = self._try(lambda: self.lib.ba_ring_arena_connect(self.handle, prv, nxt), "ba_ring_arena_connect")
+            connected: List[Optional[bool]] = [None] * self.world
+            dist.all_gather_object(connected, err is None, group=self.group)
+            if not all(connected):
+                raise CopyEngineUnavailable(err or "a peer rank could not map its neighbours' arenas")
         self.arena = torch.as_tensor(_DeviceBytes(base.value, _align(nbytes)), device=self.device)
         dist.barrier(group=self.group)
+
+    @staticmethod
+    def _try(call, what: str) -> Optional[str]:
+        """Run one C-ABI call; None on success, the error text otherwise (never raises)."""
+        try:
+            _n.check(call(), what)
+            return None
+        except _n.NativeLibraryError as e:
+            return str(e)
 
     def empty(self, shape, dtype) -> torch.Tensor:
         n = 1
@@ -199,6 +224,8 @@ def default_transport() -> str:
     env = os.environ.get("BA_RING_TRANSPORT")
     if env:
         return env
+    if _ce_disabled:
+        return "nccl"
     try:
         local = int(os.environ.get("LOCAL_WORLD_SIZE", "0"))
     except ValueError:
@@ -301,7 +328,17 @@ class Ring:
         if like.is_cuda and self.world_size > 1 and self.transport == "ce":
             self._device = like.device
             self._ensure_native(like.device)
-            self._native.begin(sum(_align(n) for n in recv_sizes))
+            try:
+                self._native.begin(sum(_align(n) for n in recv_sizes))
+            except CopyEngineUnavailable as e:
+                if os.environ.get("BA_RING_TRANSPORT") == "ce":
+                    raise  # asked for by name: fail loudly
+                # the default picked it: every rank of the ring is here together -- all fall back to NCCL
+                global _ce_disabled
+                _ce_disabled = True
+                import warnings
+                warnings.warn(f"burst_attn: copy-engine ring transport unavailable ({e}); using NCCL")
+                self.transport, self._native = "nccl", None
 
     def empty(self, shape, dtype, device) -> torch.Tensor:
         """A buffer that may be the DESTINATION of a hop on this ring."""

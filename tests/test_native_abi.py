@@ -92,3 +92,107 @@ def test_receive_arena_bump_allocator_is_symmetric_and_aligned():
     assert a.shape == (3, 5, 7) and a.dtype == torch.bfloat16 and c.is_contiguous()
     with pytest.raises(AssertionError):
         ring.empty((1,), torch.float32)  # beyond what begin() announced
+
+
+def test_copy_engine_setup_agrees_across_ranks_and_falls_back(monkeypatch):
+    """Host logic of burst_attn/comm.py around the copy-engine arena, with the C-ABI and torch.distributed faked:
+    (1) success path: create -> all-gather (ok, handle) -> connect with the NEIGHBOURS' handles -> all-gather ok;
+    (2) a rank whose create fails makes EVERY rank raise CopyEngineUnavailable after the same collectives;
+    (3) Ring.begin turns that into a process-wide switch to NCCL when the transport was only the default, and
+        re-raises when BA_RING_TRANSPORT=ce asked for it by name."""
+    import torch
+    from burst_attn import comm, native
+
+    calls = []
+
+    class FakeLib:
+        def __init__(self, fail_create=False):
+            self.fail_create = fail_create
+
+        def ba_ring_arena_create(self, handle, nbytes, base_ref, hbuf):
+            calls.append("create")
+            if self.fail_create:
+                return 2
+            hbuf[0] = 7  # this rank's "handle"
+            return 0
+
+        def ba_ring_arena_connect(self, handle, prv, nxt):
+            calls.append(("connect", prv[0], nxt[0]))
+            return 0
+
+        def ba_last_error(self):
+            return b"no CUDA IPC here"
+
+    world, rank = 4, 1
+
+    def fake_all_gather(out, obj, group=None):
+        calls.append("gather")
+        for i in range(len(out)):
+            out[i] = obj
+        if isinstance(obj, tuple):  # neighbours' handles differ from ours
+            out[(rank - 1) % world] = (peer_ok, bytes([3]) + obj[1][1:])
+            out[(rank + 1) % world] = (True, bytes([5]) + obj[1][1:])
+
+    class NoCtx:
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+
+    monkeypatch.setattr(comm.dist, "all_gather_object", fake_all_gather)
+    monkeypatch.setattr(comm.dist, "barrier", lambda group=None: calls.append("barrier"))
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda d=None: None)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: NoCtx())
+    monkeypatch.setattr(torch, "as_tensor", lambda obj, device=None: torch.zeros(obj.__cuda_array_interface__["shape"], dtype=torch.uint8))
+    fake = FakeLib()
+    monkeypatch.setattr(native, "lib", lambda: fake)
+
+    def mk(lib):
+        r = comm._NativeRing.__new__(comm._NativeRing)
+        r.lib, r.group, r.device, r.world, r.rank, r.ce = lib, None, torch.device("cpu"), world, rank, True
+        r.arena, r.arena_off, r.handle = None, 0, None
+        return r
+
+    peer_ok = True
+    ring = mk(fake)
+    ring.begin(5000)
+    assert calls == ["barrier", "create", "gather", ("connect", 3, 5), "gather", "barrier"]
+    assert ring.arena is not None and ring.arena.numel() >= 5000
+
+    calls.clear()
+    peer_ok = False  # the previous rank could not create its arena: we raise too, after the same first gather
+    with pytest.raises(comm.CopyEngineUnavailable):
+        mk(fake).begin(5000)
+    assert calls == ["barrier", "create", "gather"]
+
+    calls.clear()
+    peer_ok = True
+    bad = FakeLib(fail_create=True)
+    monkeypatch.setattr(native, "lib", lambda: bad)
+    with pytest.raises(comm.CopyEngineUnavailable, match="no CUDA IPC here"):
+        mk(bad).begin(5000)
+    assert calls == ["barrier", "create", "gather"]
+
+    # Ring.begin: default transport -> fall back to NCCL for the whole process; named transport -> re-raise
+    class FailingNative:
+        ce = True
+
+        def begin(self, n):
+            raise comm.CopyEngineUnavailable("x")
+
+    like = type("T", (), {"is_cuda": True, "device": torch.device("cpu")})()
+    monkeypatch.setattr(comm, "_ce_disabled", False)
+    monkeypatch.delenv("BA_RING_TRANSPORT", raising=False)
+    monkeypatch.setattr(comm, "get_world_size", lambda g=None: 4)
+    monkeypatch.setattr(comm, "get_rank", lambda g=None: 1)
+    r = comm.Ring(None, transport="ce")
+    r._native = FailingNative()
+    with pytest.warns(UserWarning, match="using NCCL"):
+        r.begin(like, [1024])
+    assert r.transport == "nccl" and r._native is None and comm._ce_disabled
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "4")
+    assert comm.default_transport() == "nccl"
+    monkeypatch.setattr(comm, "_ce_disabled", False)
+    monkeypatch.setenv("BA_RING_TRANSPORT", "ce")
+    r = comm.Ring(None)
+    r._native = FailingNative()
+    with pytest.raises(comm.CopyEngineUnavailable):
+        r.begin(like, [1024])
