@@ -102,7 +102,7 @@ def _mask(sq: int, sk: int, mask_mode: str, device=None) -> Optional[torch.Tenso
     raise ValueError(mask_mode)
 
 
-def chunk_forward(q, k, v, o_acc, lse, scale, mask_mode="none", dtype=torch.float64):
+def chunk_forward(q, k, v, o_acc, lse, scale, mask_mode="none", dtype=torch.float64, key_bias=None):
     """One ring round of the forward: attend q to one K/V chunk and merge into
     the running, already-normalised ``(o_acc fp, lse)`` state.
 
@@ -120,6 +120,8 @@ def chunk_forward(q, k, v, o_acc, lse, scale, mask_mode="none", dtype=torch.floa
     """
     q, k, v = (t.to(dtype) for t in (q, k, v))
     s = torch.einsum("bqhd,bkhd->bhqk", q, k) * scale
+    if key_bias is not None:  # [B|1,H,Sk] additive bias per key (the LAO tile's "vector" bias, lao.py:155-173)
+        s = s + key_bias.to(dtype).unsqueeze(2)
     m = _mask(s.shape[-2], s.shape[-1], mask_mode)
     if m is not None:
         s = s.masked_fill(~m, NEG_INF)
@@ -146,7 +148,7 @@ def compute_delta(o, do, dtype=torch.float64):
     return (o.to(dtype) * do.to(dtype)).sum(-1).permute(0, 2, 1).contiguous()
 
 
-def chunk_backward(do, q, k, v, delta, lse, scale, mask_mode="none", dtype=torch.float64):
+def chunk_backward(do, q, k, v, delta, lse, scale, mask_mode="none", dtype=torch.float64, key_bias=None):
     """One ring round of the backward for one (Q-bundle, K/V) pair.
 
     Follows inter_normal_attn_backward (burst_utils.py:77-100), the reference's
@@ -158,6 +160,8 @@ def chunk_backward(do, q, k, v, delta, lse, scale, mask_mode="none", dtype=torch
     """
     do, q, k, v, delta, lse = (t.to(dtype) for t in (do, q, k, v, delta, lse))
     s = torch.einsum("bqhd,bkhd->bhqk", q, k) * scale
+    if key_bias is not None:
+        s = s + key_bias.to(dtype).unsqueeze(2)
     p = torch.exp(s - lse.unsqueeze(-1))
     m = _mask(s.shape[-2], s.shape[-1], mask_mode)
     if m is not None:

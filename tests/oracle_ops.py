@@ -25,13 +25,13 @@ class OracleOps:
         self.launches = 0
         self.calls = []
 
-    def fwd_chunk(self, q, k, v, o_acc, lse, o_out, scale, causal, causal_offset, first, last, seq_dim):
+    def fwd_chunk(self, q, k, v, o_acc, lse, o_out, scale, causal, causal_offset, first, last, seq_dim, bias=None):
         self.calls.append(("fwd", tuple(q.shape), tuple(k.shape), causal, causal_offset, first, last))
         qq, kk, vv = (_bshd(t, seq_dim) for t in (q, k, v))
         mode = _mode(causal, causal_offset, qq.shape[1], kk.shape[1])
         st_o = None if first else _bshd(o_acc, seq_dim).double()
         st_l = None if first else lse.double()
-        o, l = orc.chunk_forward(qq, kk, vv, st_o, st_l, scale, mode)
+        o, l = orc.chunk_forward(qq, kk, vv, st_o, st_l, scale, mode, key_bias=bias)
         lse.copy_(l.to(lse.dtype))
         if last:
             _bshd(o_out, seq_dim).copy_(o.to(o_out.dtype))
@@ -44,12 +44,12 @@ class OracleOps:
         self.launches += 1
 
     def bwd_chunk(self, d_o, q, k, v, delta, lse, dq_acc, dk_acc, dv_acc, scale, causal, causal_offset, seq_dim,
-                  deterministic=False):
+                  deterministic=False, bias=None):
         self.calls.append(("bwd", tuple(q.shape), tuple(k.shape), causal, causal_offset))
         g, qq, kk, vv = (_bshd(t, seq_dim) for t in (d_o, q, k, v))
         mode = _mode(causal, causal_offset, qq.shape[1], kk.shape[1])
         ls = torch.where(torch.isinf(lse), torch.full_like(lse, 1e30), lse)
-        dq, dk, dv = orc.chunk_backward(g, qq, kk, vv, delta, ls, scale, mode)
+        dq, dk, dv = orc.chunk_backward(g, qq, kk, vv, delta, ls, scale, mode, key_bias=bias)
         _bshd(dq_acc, seq_dim).add_(dq.to(dq_acc.dtype))
         _bshd(dk_acc, seq_dim).add_(dk.to(dk_acc.dtype))
         _bshd(dv_acc, seq_dim).add_(dv.to(dv_acc.dtype))

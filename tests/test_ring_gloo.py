@@ -370,3 +370,54 @@ def test_ring_driver_with_l2_blocking_world2(case, monkeypatch):
         errs.append(errq.get())
     assert not errs, "\n".join(errs)
     assert all(p.exitcode == 0 for p in procs)
+
+
+@pytest.mark.parametrize("blk", [16, 1000])
+def test_single_gpu_wrappers_packed_bias_blocked_cpu(monkeypatch, blk):
+    """burst_attn.flash_triton (flash_attn_func / _kvpacked_func / _qkvpacked_func): strided views of the packed
+    tensors, bottom-right-aligned causal with Sq != Sk, per-key bias narrowed per L2 block -- the Python logic,
+    on CPU with oracle-backed chunk operators, against dense attention."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from burst_attn import chunk_ops
+    from burst_attn.flash_triton import flash_attn_func, flash_attn_kvpacked_func, flash_attn_qkvpacked_func
+    from oracle import attention_oracle as orc
+    from oracle_ops import OracleOps
+    monkeypatch.setenv("BA_L2_BLOCK", str(blk))
+    ops = OracleOps()
+    ops.tile_head_dims = (16,)
+    chunk_ops._set_ops_for_testing(ops)
+    try:
+        torch.manual_seed(11)
+        B, S, H, D = 2, 70, 2, 16
+        qkv = torch.randn(B, S, 3, H, D, dtype=torch.float64)
+        do = torch.randn(B, S, H, D, dtype=torch.float64)
+        bias = torch.randn(1, H, 1, S, dtype=torch.float64)
+        bias[..., 3::5] = float("-inf")
+        q, k, v = (qkv[:, :, i].contiguous() for i in range(3))
+        for causal in (False, True):
+            o_ref, _, dq, dk, dv = orc.dense_attention_bwd(q, k, v, do, None, causal, bias=bias)
+            p = qkv.clone().requires_grad_()
+            o = flash_attn_qkvpacked_func(p, bias, causal)
+            (dqkv,) = torch.autograd.grad(o, (p,), do)
+            torch.testing.assert_close(o.detach(), o_ref, rtol=1e-5, atol=1e-5)
+            for i, r in enumerate((dq, dk, dv)):
+                torch.testing.assert_close(dqkv[:, :, i], r, rtol=1e-5, atol=1e-5)
+            qq, kv = q.clone().requires_grad_(), qkv[:, :, 1:].clone().requires_grad_()
+            o = flash_attn_kvpacked_func(qq, kv, bias, causal)
+            gq, gkv = torch.autograd.grad(o, (qq, kv), do)
+            torch.testing.assert_close(gq, dq, rtol=1e-5, atol=1e-5)
+            torch.testing.assert_close(gkv[:, :, 0], dk, rtol=1e-5, atol=1e-5)
+            torch.testing.assert_close(gkv[:, :, 1], dv, rtol=1e-5, atol=1e-5)
+        # Sq != Sk, causal aligned bottom-right (the last query sees every key), no bias
+        qs, dos = q[:, 30:].contiguous(), do[:, 30:].contiguous()
+        o_ref, _, dq, dk, dv = orc.dense_attention_bwd(qs, k, v, dos, None, True)
+        qq, kk, vv = (t.clone().requires_grad_() for t in (qs, k, v))
+        o = flash_attn_func(qq, kk, vv, None, True)
+        g = torch.autograd.grad(o, (qq, kk, vv), dos)
+        torch.testing.assert_close(o.detach(), o_ref, rtol=1e-5, atol=1e-5)
+        for a, r in zip(g, (dq, dk, dv)):
+            torch.testing.assert_close(a, r, rtol=1e-5, atol=1e-5)
+        with pytest.raises(NotImplementedError):
+            flash_attn_func(qq, kk, vv, torch.zeros(1, H, 40, S), False)
+    finally:
+        chunk_ops._set_ops_for_testing(None)
