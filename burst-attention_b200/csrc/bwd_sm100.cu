@@ -9,15 +9,16 @@
 //
 // One CTA owns one 128-key block of the home K/V chunk for one (batch, head)
 // and loops over the 128-row blocks of the visiting Q-bundle:
-//   S^T  = K Q_i^T           (SS; TMEM rows = keys, cols = queries)
-//   dP^T = V dO_i^T          (SS)
-//   P^T  = exp2(S^T*c - lse) , dS^T = P^T o (dP^T - delta)      (8 compute warps, thread = key row)
+//   S^T  = K Q_i^T - lse/scale   (SS; TMEM rows = keys, cols = queries; the row statistic is one extra K = 16 step)
+//   dP^T = V dO_i^T - delta      (SS; same)
+//   P^T  = exp2(S^T*c [+ bias]) , dS^T = P^T o dP^T             (8 compute warps, thread = key row)
 //   dV  += P^T dO_i          (TS; P^T 16-bit in TMEM aliasing S^T)
-//   dK  += dS^T Q_i          (SS; dS^T staged once in smem, read K-major)
-//   dQ_i = dS K              (SS; the same smem tile read MN-major) -> TMEM (aliasing dP^T)
+//   dK  += dS^T Q_i          (TS; dS^T 16-bit in TMEM over the consumed dP^T columns)
+//   dQ_i = dS K              (SS; dS^T also staged once in smem, read MN-major) -> TMEM (aliasing dP^T)
 //   dQ_i -> 4 reduce warps -> smem -> cp.reduce.async.bulk.tensor (fp32 add in L2) -> dq_acc
-// TMEM (512 cols): S^T/P^T [0,128)  dP^T/dQ [128,256)  dK [256,384)  dV [384,512).
-// smem: K 32K, V 32K, Q 2x32K, dO 32K, dS 32K, dQ staging 2x16K, row stats 2x1K.
+// TMEM (512 cols): S^T/P^T [0,128)  dP^T/dS^T/dQ [128,256)  dK [256,256+D)  dV [384,384+D).
+// smem (D = 128): K 32K, V 32K, Q 2x32K, dO 32K, dS 32K, dQ staging 2x16K, row-stat operand tile 2K (+640 B constants).
+// Head dim D = 64 or 128 (template): the operand tiles shrink to one SW128 box, N = D for dV / dK / dQ.
 #include <math.h>
 #include <stdlib.h>
 
@@ -290,9 +291,9 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp == 12) {
     // ============================================================ MMA issuer
-    // (A/B on one box: a fully unrolled constant-descriptor issue path like the forward's made this
-    //  kernel 7 % SLOWER -- 953 vs 1026 TFLOP/s -- the backward is bound by shared-memory operand
-    //  bandwidth, not by issue rate, so the compact rolled form below is kept.)
+    // (A/B on one box, round 1: a fully unrolled constant-descriptor issue path like the forward's made this
+    //  kernel 7 % SLOWER -- 953 vs 1026 TFLOP/s -- so the compact rolled form below is kept.  What bounds the
+    //  kernel is the dependency chain between this warp and its consumers)
     reg_dec<64>();
     {
       constexpr uint32_t id_kk = make_idesc(kBF16, 128, 128, false, false);  // A K-major, B K-major
@@ -338,10 +339,9 @@ bwd_chunk_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           umma_ts(tDV, tS + (kk >> 2) * 64 + (kk & 3) * 8, desc_advance(dDO_n, kstep_n(kk)), id_kn, acc || kk > 0);
       };
       // dK += dS^T Q with dS^T (16-bit) read from TMEM, where the compute warps left it over the
-      // dP^T columns they had just consumed (q 0..63 at [128,160), q 64..127 at [192,224)).  TS form:
-      // only Q_i (4 KiB per MMA) comes from shared memory -- tcgen05 fetches smem operands at only
-      // ~64 B/clk, so an SS MMA with 8 KiB of operands runs at about half rate.  The dQ MMA issued
-      // right behind overwrites these columns; the tensor pipe executes in order, so that is safe.
+      // dP^T columns they had just consumed (q 0..63 at [128,160), q 64..127 at [192,224)).  TS form: a K = 16
+      // step with A in TMEM costs N/2 = 64 clk, with A in shared memory max(74, N/2) (tools/ubench.py).  The dQ MMA
+      // issued right behind overwrites these columns; the tensor pipe executes in order, so that is safe.
       auto issue_dK = [&](int st, bool acc) {
         const uint64_t dQ_n = make_smem_desc(smem_u32(sQ + st * kTileB), kBoxB, 1024);
 #pragma unroll
